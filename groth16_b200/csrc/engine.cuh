@@ -1,0 +1,717 @@
+// engine.cuh -- per-curve host orchestration of the proving hot path behind the C ABI (include/g16b200.h).
+//
+// Mirrors, function by function, what /root/reference does between `create_proof_with_reduction_and_matrices`
+// (prover.rs:26-51) and `Proof{a,b,c}` (prover.rs:127-131); the heavy steps are the CUDA kernels of ntt.cuh and
+// msm.cuh, the O(1) tail (six scalar multiplications, sums, into_affine) runs on the host with the same field code.
+#pragma once
+#include <cuda_runtime.h>
+#include <chrono>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include "../../include/g16b200.h"
+#include "ec.cuh"
+#include "msm.cuh"
+#include "ntt.cuh"
+
+namespace g16 {
+
+std::string& last_error_ref();
+inline int fail(int code, const std::string& msg) {
+  last_error_ref() = msg;
+  return code;
+}
+#define G16_CUDA(x)                                                                                       \
+  do {                                                                                                    \
+    cudaError_t _e = (x);                                                                                 \
+    if (_e != cudaSuccess)                                                                                \
+      return fail(G16_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(_e) + " @" + __FILE__ + ":" + \
+                                    std::to_string(__LINE__));                                            \
+  } while (0)
+
+struct IEngine {
+  virtual ~IEngine() {}
+  virtual int fq_limbs() const = 0;
+  virtual int partial_limbs() const = 0;
+  virtual int ntt(uint32_t log_n, int inverse, int coset, uint64_t* inout) = 0;
+  virtual int witness_map_evals(uint32_t log_n, const uint64_t* a, const uint64_t* b, const uint64_t* c, uint64_t* h) = 0;
+  virtual int msm_g1(const uint64_t* bases, const uint64_t* scalars, uint64_t n, uint64_t* out) = 0;
+  virtual int msm_g2(const uint64_t* bases, const uint64_t* scalars, uint64_t n, uint64_t* out) = 0;
+  virtual int circuit_load(uint32_t ni, uint32_t nc, uint32_t nw, const g16_csr* a, const g16_csr* b, const g16_csr* c) = 0;
+  virtual int pk_load(const g16_pk_desc* pk, uint32_t rank, uint32_t world) = 0;
+  virtual int setup(const uint64_t* alpha, const uint64_t* beta, const uint64_t* gamma, const uint64_t* delta,
+                    const uint64_t* tau, const uint64_t* g1, const uint64_t* g2) = 0;
+  virtual int pk_export(const g16_pk_export_desc* out) = 0;
+  virtual int prove(const uint64_t* r, const uint64_t* s, const uint64_t* z, uint32_t flags, uint64_t* proof) = 0;
+  virtual int prove_partial(const uint64_t* r, const uint64_t* z, uint32_t flags, uint64_t* partial) = 0;
+  virtual int prove_assemble(const uint64_t* r, const uint64_t* s, const uint64_t* partials, uint32_t nparts, uint64_t* proof) = 0;
+  virtual int witness_map(const uint64_t* z, uint32_t flags, uint64_t* h) = 0;
+  virtual uint32_t domain_log() const = 0;
+  g16_timings tm{};
+};
+
+// ------------------------------------------------------------------------------------------------
+// fixed-base batch multiplication (BatchMulPreprocessing::batch_mul, generator.rs:129-183)
+// ------------------------------------------------------------------------------------------------
+static constexpr int FB_WINDOWS = 32;  // 8-bit windows over a 256-bit scalar
+template <class F>
+__global__ void fb_table_kernel(Affine<F> g, XYZZ<F>* table /* [32][255] */) {
+  const int w = threadIdx.x;
+  if (w >= FB_WINDOWS) return;
+  XYZZ<F> base = XYZZ<F>::from_affine(g);
+  for (int i = 0; i < 8 * w; i++) base.dbl_inplace();
+  XYZZ<F> acc = base;
+  for (int d = 1; d <= 255; d++) {
+    table[w * 255 + d - 1] = acc;
+    acc.add(base);
+  }
+}
+template <class F, class FrF>
+__global__ void __launch_bounds__(128) fb_mul_kernel(const XYZZ<F>* __restrict__ table, const FrF* __restrict__ scalars,
+                                                     uint32_t n, Affine<F>* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const FrF s = FrF::from_mont(ntt_ldg(scalars + i));
+  XYZZ<F> acc = XYZZ<F>::inf();
+  for (int w = 0; w < FB_WINDOWS; w++) {
+    const uint32_t d = (s.v[w >> 2] >> (8 * (w & 3))) & 0xff;
+    if (d) acc.add(table[w * 255 + d - 1]);
+  }
+  out[i] = acc.to_affine();
+}
+
+// ------------------------------------------------------------------------------------------------
+template <class CP>
+struct Engine : IEngine {
+  using Fr = Fp<typename CP::FrP>;
+  using Fq = Fp<typename CP::FqP>;
+  using Fq2 = Fp2<typename CP::FqP, CP::FQ2_NONRESIDUE_NEG>;
+  using A1 = Affine<Fq>;
+  using A2 = Affine<Fq2>;
+  using P1 = XYZZ<Fq>;
+  using P2 = XYZZ<Fq2>;
+  static constexpr int NQ64 = Fq::N / 2;
+  static constexpr int FR_BITS = CP::FrP::BITS;
+  enum { M_H = 0, M_L = 1, M_A = 2, M_B1 = 3, M_B2 = 4 };
+
+  int device = 0;
+  cudaStream_t st_main = nullptr, st_msm[5] = {};
+  cudaEvent_t ev_start = nullptr, ev_z = nullptr, ev_h = nullptr, ev_m0[5] = {}, ev_m1[5] = {}, ev_a0[5] = {}, ev_a1[5] = {};
+  NttDomain<Fr> dom;
+  DevBuf d_z, d_a, d_b, d_c, d_t, d_h;
+  MsmWorkspace<Fq> ws1[4];
+  MsmWorkspace<Fq2> ws2;
+  MsmCounters ctr;
+  unsigned long long ntt_launches = 0;
+
+  // resident circuit
+  bool have_circuit = false;
+  uint32_t num_inputs = 0, num_constraints = 0, num_witness = 0;
+  int L = 0;
+  DevBuf csr_rp[3], csr_col[3], csr_val[3];
+  std::vector<uint32_t> h_rp[3], h_col[3];   // host copies kept for g16_setup
+  std::vector<Fr> h_val[3];
+
+  // resident proving key (this rank's shard)
+  bool have_pk = false;
+  uint32_t rank = 0, world = 1;
+  struct Query {
+    DevBuf bases, mask;
+    uint64_t pairs = 0;   // full MSM length
+    uint64_t lo = 0, hi = 0;
+  } q[5];
+  A1 a0, b1_0, alpha_g1, beta_g1, delta_g1;
+  A2 b2_0, beta_g2, delta_g2;
+  // setup-only extras for pk_export
+  A2 gamma_g2;
+  DevBuf d_gamma_abc;
+  bool from_setup = false;
+  DevBuf full_a, full_b1, full_b2;  // setup keeps element 0 too, for export
+
+  // ------------------------------------------------------------------
+  int init(int dev) {
+    device = dev;
+    G16_CUDA(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    G16_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10) return fail(G16_ERR_CUDA, "device is not sm_100-class (this library ships sm_100a code only)");
+    G16_CUDA(cudaStreamCreateWithFlags(&st_main, cudaStreamNonBlocking));
+    for (int i = 0; i < 5; i++) G16_CUDA(cudaStreamCreateWithFlags(&st_msm[i], cudaStreamNonBlocking));
+    G16_CUDA(cudaEventCreate(&ev_start));
+    G16_CUDA(cudaEventCreate(&ev_z));
+    G16_CUDA(cudaEventCreate(&ev_h));
+    for (int i = 0; i < 5; i++) {
+      G16_CUDA(cudaEventCreate(&ev_m0[i]));
+      G16_CUDA(cudaEventCreate(&ev_m1[i]));
+      G16_CUDA(cudaEventCreate(&ev_a0[i]));
+      G16_CUDA(cudaEventCreate(&ev_a1[i]));
+    }
+    return G16_OK;
+  }
+  ~Engine() override {
+    cudaSetDevice(device);
+    cudaDeviceSynchronize();
+    dom.release();
+    d_z.release(); d_a.release(); d_b.release(); d_c.release(); d_t.release(); d_h.release();
+    for (auto& w : ws1) w.release();
+    ws2.release();
+    for (int m = 0; m < 3; m++) { csr_rp[m].release(); csr_col[m].release(); csr_val[m].release(); }
+    for (auto& x : q) { x.bases.release(); x.mask.release(); }
+    d_gamma_abc.release(); full_a.release(); full_b1.release(); full_b2.release();
+    if (st_main) cudaStreamDestroy(st_main);
+    for (auto s : st_msm) if (s) cudaStreamDestroy(s);
+    for (cudaEvent_t e : {ev_start, ev_z, ev_h}) if (e) cudaEventDestroy(e);
+    for (int i = 0; i < 5; i++) for (cudaEvent_t e : {ev_m0[i], ev_m1[i], ev_a0[i], ev_a1[i]}) if (e) cudaEventDestroy(e);
+  }
+  int fq_limbs() const override { return NQ64; }
+  int partial_limbs() const override { return 4 * 2 * NQ64 + 4 * NQ64; }
+  uint32_t domain_log() const override { return (uint32_t)L; }
+
+  // ---- small host helpers ----
+  static Fr load_fr(const uint64_t* p) { Fr r; memcpy(r.v, p, sizeof(r.v)); return r; }
+  static A1 load_a1(const uint64_t* p) { A1 r; memcpy(&r.x, p, sizeof(Fq)); memcpy(&r.y, p + NQ64, sizeof(Fq)); return r; }
+  static A2 load_a2(const uint64_t* p) {
+    A2 r;
+    memcpy(&r.x.c0, p, sizeof(Fq)); memcpy(&r.x.c1, p + NQ64, sizeof(Fq));
+    memcpy(&r.y.c0, p + 2 * NQ64, sizeof(Fq)); memcpy(&r.y.c1, p + 3 * NQ64, sizeof(Fq));
+    return r;
+  }
+  static void store_a1(uint64_t* p, const A1& a) { memcpy(p, &a.x, sizeof(Fq)); memcpy(p + NQ64, &a.y, sizeof(Fq)); }
+  static void store_a2(uint64_t* p, const A2& a) {
+    memcpy(p, &a.x.c0, sizeof(Fq)); memcpy(p + NQ64, &a.x.c1, sizeof(Fq));
+    memcpy(p + 2 * NQ64, &a.y.c0, sizeof(Fq)); memcpy(p + 3 * NQ64, &a.y.c1, sizeof(Fq));
+  }
+  // Jacobian normalised to Z = 1 (identity: (1,1,0) like ark)
+  template <class F, class PT>
+  static void store_proj(uint64_t* p, const PT& pt) {
+    Affine<F> a = pt.to_affine();
+    F one = F::one(), zero = F::zero();
+    const size_t w = sizeof(F) / 8;
+    if (pt.is_inf()) { memcpy(p, &one, sizeof(F)); memcpy(p + w, &one, sizeof(F)); memcpy(p + 2 * w, &zero, sizeof(F)); }
+    else { memcpy(p, &a.x, sizeof(F)); memcpy(p + w, &a.y, sizeof(F)); memcpy(p + 2 * w, &one, sizeof(F)); }
+  }
+  static void fr_to_canon(const Fr& m, uint32_t out[8]) {
+    Fr c = Fr::from_mont(m);
+    memcpy(out, c.v, 32);
+  }
+  static int check_log(uint32_t log_n) {
+    if ((int)log_n > CP::FrP::TWO_ADICITY) return fail(G16_ERR_POLYNOMIAL_DEGREE_TOO_LARGE, "domain size exceeds the field's two-adicity (PolynomialDegreeTooLarge)");
+    if (log_n > 28) return fail(G16_ERR_BAD_ARGUMENT, "log_n > 28 unsupported");
+    return G16_OK;
+  }
+
+  // ---- domain + buffers ----
+  int ensure_domain(int Ln) {
+    if (dom.L != Ln) {
+      G16_CUDA(cudaStreamSynchronize(st_main));
+      G16_CUDA(ntt_domain_build(dom, Ln, st_main, &ntt_launches));
+    }
+    const size_t bytes = (size_t)sizeof(Fr) << Ln;
+    G16_CUDA(d_a.reserve(bytes)); G16_CUDA(d_b.reserve(bytes)); G16_CUDA(d_c.reserve(bytes));
+    G16_CUDA(d_t.reserve(bytes)); G16_CUDA(d_h.reserve(bytes));
+    return G16_OK;
+  }
+
+  // ---- NTT API ----
+  int ntt(uint32_t log_n, int inverse, int coset, uint64_t* inout) override {
+    if (!inout) return fail(G16_ERR_BAD_ARGUMENT, "null buffer");
+    int rc = check_log(log_n);
+    if (rc) return rc;
+    G16_CUDA(cudaSetDevice(device));
+    if ((rc = ensure_domain((int)log_n))) return rc;
+    const size_t bytes = (size_t)sizeof(Fr) << log_n;
+    Fr* x = d_a.template as<Fr>();
+    Fr* y = d_t.template as<Fr>();
+    G16_CUDA(cudaMemcpyAsync(x, inout, bytes, cudaMemcpyHostToDevice, st_main));
+    const Fr zero = Fr::zero();
+    if (!inverse)
+      ntt_run<Fr>(st_main, dom, false, x, x, y, coset ? NTT_LOAD_MUL_TABLE : NTT_LOAD_PLAIN, dom.coset_fwd, nullptr, nullptr, zero,
+                  NTT_STORE_PLAIN, nullptr, zero, &ntt_launches);
+    else
+      ntt_run<Fr>(st_main, dom, true, x, x, y, NTT_LOAD_PLAIN, nullptr, nullptr, nullptr, zero,
+                  coset ? NTT_STORE_MUL_TABLE : NTT_STORE_MUL_CONST, dom.coset_inv, dom.n_inv, &ntt_launches);
+    G16_CUDA(cudaGetLastError());
+    G16_CUDA(cudaMemcpyAsync(inout, y, bytes, cudaMemcpyDeviceToHost, st_main));
+    G16_CUDA(cudaStreamSynchronize(st_main));
+    return G16_OK;
+  }
+
+  // a, b, c (device, evaluations over the domain) -> d_h (coefficients of h).  r1cs_to_qap.rs:201-232
+  void witness_map_device() {
+    Fr* A = d_a.template as<Fr>(); Fr* B = d_b.template as<Fr>(); Fr* C = d_c.template as<Fr>(); Fr* T = d_t.template as<Fr>(); Fr* H = d_h.template as<Fr>();
+    const Fr zero = Fr::zero();
+    for (Fr* X : {A, B, C}) {
+      // domain.ifft_in_place (r1cs_to_qap.rs:201-202,220)
+      ntt_run<Fr>(st_main, dom, true, X, X, T, NTT_LOAD_PLAIN, nullptr, nullptr, nullptr, zero, NTT_STORE_MUL_CONST, nullptr, dom.n_inv, &ntt_launches);
+      // coset_domain.fft_in_place (r1cs_to_qap.rs:204-207,221)
+      ntt_run<Fr>(st_main, dom, false, T, T, X, NTT_LOAD_MUL_TABLE, dom.coset_fwd, nullptr, nullptr, zero, NTT_STORE_PLAIN, nullptr, zero, &ntt_launches);
+    }
+    // (a*b - c) * Z^-1 fused into the load of coset_domain.ifft_in_place (r1cs_to_qap.rs:209,223-232)
+    ntt_run<Fr>(st_main, dom, true, A, T, H, NTT_LOAD_AB_MINUS_C, nullptr, B, C, dom.z_inv, NTT_STORE_MUL_TABLE, dom.coset_inv, zero, &ntt_launches);
+  }
+
+  int witness_map_evals(uint32_t log_n, const uint64_t* a, const uint64_t* b, const uint64_t* c, uint64_t* h) override {
+    if (!a || !b || !c || !h) return fail(G16_ERR_BAD_ARGUMENT, "null buffer");
+    int rc = check_log(log_n);
+    if (rc) return rc;
+    G16_CUDA(cudaSetDevice(device));
+    if ((rc = ensure_domain((int)log_n))) return rc;
+    const size_t bytes = (size_t)sizeof(Fr) << log_n;
+    G16_CUDA(cudaMemcpyAsync(d_a.p, a, bytes, cudaMemcpyHostToDevice, st_main));
+    G16_CUDA(cudaMemcpyAsync(d_b.p, b, bytes, cudaMemcpyHostToDevice, st_main));
+    G16_CUDA(cudaMemcpyAsync(d_c.p, c, bytes, cudaMemcpyHostToDevice, st_main));
+    witness_map_device();
+    G16_CUDA(cudaGetLastError());
+    G16_CUDA(cudaMemcpyAsync(h, d_h.p, bytes, cudaMemcpyDeviceToHost, st_main));
+    G16_CUDA(cudaStreamSynchronize(st_main));
+    return G16_OK;
+  }
+
+  // ---- stand-alone MSM API (msm_bigint) ----
+  template <class F, class WS>
+  int msm_host(WS& ws, const uint64_t* bases, const uint64_t* scalars, uint64_t n, uint64_t* out) {
+    if (!out || (n && (!bases || !scalars))) return fail(G16_ERR_BAD_ARGUMENT, "null buffer");
+    if (n >= (1ull << 27)) return fail(G16_ERR_BAD_ARGUMENT, "n too large");
+    G16_CUDA(cudaSetDevice(device));
+    XYZZ<F> res = XYZZ<F>::inf();
+    if (n) {
+      DevBuf db, ds, dm;
+      G16_CUDA(db.reserve(n * sizeof(Affine<F>)));
+      G16_CUDA(ds.reserve(n * 32));
+      G16_CUDA(dm.reserve(n));
+      G16_CUDA(cudaMemcpyAsync(db.p, bases, n * sizeof(Affine<F>), cudaMemcpyHostToDevice, st_main));
+      G16_CUDA(cudaMemcpyAsync(ds.p, scalars, n * 32, cudaMemcpyHostToDevice, st_main));
+      msm_inf_mask<F><<<(unsigned)((n + 255) / 256), 256, 0, st_main>>>(db.template as<Affine<F>>(), (uint32_t)n, dm.template as<uint8_t>());
+      const MsmGeom g = msm_geom(n, FR_BITS);
+      cudaError_t e = msm_enqueue<F, Fr>(st_main, ws, g, db.template as<Affine<F>>(), dm.template as<uint8_t>(), ds.template as<uint32_t>(), false, &ctr);
+      if (e != cudaSuccess) { db.release(); ds.release(); dm.release(); return fail(G16_ERR_CUDA, std::string("msm_enqueue: ") + cudaGetErrorString(e)); }
+      e = cudaStreamSynchronize(st_main);
+      db.release(); ds.release(); dm.release();
+      if (e != cudaSuccess) return fail(G16_ERR_CUDA, std::string("msm sync: ") + cudaGetErrorString(e));
+      res = msm_finish<F>(ws, g);
+    }
+    store_proj<F>(out, res);
+    return G16_OK;
+  }
+  int msm_g1(const uint64_t* bases, const uint64_t* scalars, uint64_t n, uint64_t* out) override { return msm_host<Fq>(ws1[0], bases, scalars, n, out); }
+  int msm_g2(const uint64_t* bases, const uint64_t* scalars, uint64_t n, uint64_t* out) override { return msm_host<Fq2>(ws2, bases, scalars, n, out); }
+
+  // ---- circuit ----
+  int circuit_load(uint32_t ni, uint32_t nc, uint32_t nw, const g16_csr* a, const g16_csr* b, const g16_csr* c) override {
+    if (!a || !b || !c || ni == 0) return fail(G16_ERR_BAD_ARGUMENT, "bad circuit description");
+    uint64_t need = (uint64_t)nc + ni;
+    int Ln = 0;
+    while ((1ull << Ln) < need) Ln++;
+    int rc = check_log((uint32_t)Ln);
+    if (rc) return rc;
+    G16_CUDA(cudaSetDevice(device));
+    const g16_csr* ms[3] = {a, b, c};
+    const uint32_t nvars = ni + nw;
+    for (int m = 0; m < 3; m++) {
+      if (!ms[m]->row_ptr) return fail(G16_ERR_BAD_ARGUMENT, "null row_ptr");
+      const uint32_t nnz = ms[m]->row_ptr[nc];
+      if (nnz && (!ms[m]->col || !ms[m]->val)) return fail(G16_ERR_BAD_ARGUMENT, "null col/val");
+      for (uint32_t e = 0; e < nnz; e++) if (ms[m]->col[e] >= nvars) return fail(G16_ERR_BAD_ARGUMENT, "column index out of range");
+      h_rp[m].assign(ms[m]->row_ptr, ms[m]->row_ptr + nc + 1);
+      h_col[m].assign(ms[m]->col, ms[m]->col + nnz);
+      h_val[m].resize(nnz);
+      if (nnz) memcpy(h_val[m].data(), ms[m]->val, (size_t)nnz * 32);
+      G16_CUDA(csr_rp[m].reserve((size_t)(nc + 1) * 4));
+      G16_CUDA(csr_col[m].reserve((size_t)nnz * 4 + 4));
+      G16_CUDA(csr_val[m].reserve((size_t)nnz * 32 + 32));
+      G16_CUDA(cudaMemcpy(csr_rp[m].p, ms[m]->row_ptr, (size_t)(nc + 1) * 4, cudaMemcpyHostToDevice));
+      if (nnz) {
+        G16_CUDA(cudaMemcpy(csr_col[m].p, ms[m]->col, (size_t)nnz * 4, cudaMemcpyHostToDevice));
+        G16_CUDA(cudaMemcpy(csr_val[m].p, ms[m]->val, (size_t)nnz * 32, cudaMemcpyHostToDevice));
+      }
+    }
+    num_inputs = ni; num_constraints = nc; num_witness = nw; L = Ln;
+    G16_CUDA(d_z.reserve((size_t)nvars * 32));
+    if ((rc = ensure_domain(L))) return rc;
+    G16_CUDA(cudaStreamSynchronize(st_main));
+    have_circuit = true;
+    have_pk = false;
+    return G16_OK;
+  }
+
+  // ---- proving key ----
+  void shard(Query& x, uint64_t pairs) {
+    x.pairs = pairs;
+    x.lo = pairs * rank / world;
+    x.hi = pairs * (rank + 1) / world;
+  }
+  template <class F>
+  int upload_query(Query& x, const uint64_t* host_full, uint64_t skip_first) {
+    using AT = Affine<F>;
+    const uint64_t cnt = x.hi - x.lo;
+    G16_CUDA(x.bases.reserve(cnt * sizeof(AT) + 16));
+    G16_CUDA(x.mask.reserve(cnt + 16));
+    if (cnt) {
+      const size_t limbs = sizeof(AT) / 8;
+      G16_CUDA(cudaMemcpy(x.bases.p, host_full + (skip_first + x.lo) * limbs, cnt * sizeof(AT), cudaMemcpyHostToDevice));
+      msm_inf_mask<F><<<(unsigned)((cnt + 255) / 256), 256, 0, st_main>>>(x.bases.template as<AT>(), (uint32_t)cnt, x.mask.template as<uint8_t>());
+      G16_CUDA(cudaGetLastError());
+    }
+    return G16_OK;
+  }
+  uint64_t nvars() const { return (uint64_t)num_inputs + num_witness; }
+  int pk_load(const g16_pk_desc* pk, uint32_t rk, uint32_t wd) override {
+    if (!have_circuit) return fail(G16_ERR_BAD_ARGUMENT, "g16_circuit_load must precede g16_pk_load");
+    if (!pk || wd == 0 || rk >= wd) return fail(G16_ERR_BAD_ARGUMENT, "bad pk / rank / world");
+    if (!pk->a_query || !pk->b_g1_query || !pk->b_g2_query || !pk->alpha_g1 || !pk->beta_g1 || !pk->delta_g1 || !pk->beta_g2 || !pk->delta_g2)
+      return fail(G16_ERR_BAD_ARGUMENT, "null pk member");
+    if (pk->a_len < 1 || pk->b_g1_len < 1 || pk->b_g2_len < 1) return fail(G16_ERR_MALFORMED_KEY, "a/b queries must hold at least the constant-one base");
+    if ((pk->h_len && !pk->h_query) || (pk->l_len && !pk->l_query)) return fail(G16_ERR_BAD_ARGUMENT, "null h/l query");
+    G16_CUDA(cudaSetDevice(device));
+    rank = rk; world = wd;
+    const uint64_t n = 1ull << L;
+    const uint64_t nz1 = nvars() - 1;  // |input_assignment ++ aux_assignment|, prover.rs:85
+    // msm_bigint truncates to the shorter operand (relied upon at prover.rs:66)
+    shard(q[M_H], std::min<uint64_t>(pk->h_len, n));
+    shard(q[M_L], std::min<uint64_t>(pk->l_len, num_witness));
+    shard(q[M_A], std::min<uint64_t>(pk->a_len - 1, nz1));
+    shard(q[M_B1], std::min<uint64_t>(pk->b_g1_len - 1, nz1));
+    shard(q[M_B2], std::min<uint64_t>(pk->b_g2_len - 1, nz1));
+    int rc;
+    if ((rc = upload_query<Fq>(q[M_H], pk->h_query, 0))) return rc;
+    if ((rc = upload_query<Fq>(q[M_L], pk->l_query, 0))) return rc;
+    if ((rc = upload_query<Fq>(q[M_A], pk->a_query, 1))) return rc;
+    if ((rc = upload_query<Fq>(q[M_B1], pk->b_g1_query, 1))) return rc;
+    if ((rc = upload_query<Fq2>(q[M_B2], pk->b_g2_query, 1))) return rc;
+    a0 = load_a1(pk->a_query); b1_0 = load_a1(pk->b_g1_query); b2_0 = load_a2(pk->b_g2_query);
+    alpha_g1 = load_a1(pk->alpha_g1); beta_g1 = load_a1(pk->beta_g1); delta_g1 = load_a1(pk->delta_g1);
+    beta_g2 = load_a2(pk->beta_g2); delta_g2 = load_a2(pk->delta_g2);
+    G16_CUDA(cudaStreamSynchronize(st_main));
+    have_pk = true;
+    from_setup = false;
+    return G16_OK;
+  }
+
+  // ---- setup (generator.rs:47-208) ----
+  template <class F>
+  int batch_mul(const Affine<F>& gen, const Fr* d_scalars, uint64_t cnt, Affine<F>* d_out, DevBuf& table) {
+    G16_CUDA(table.reserve((size_t)FB_WINDOWS * 255 * sizeof(XYZZ<F>)));
+    fb_table_kernel<F><<<1, 32, 0, st_main>>>(gen, table.template as<XYZZ<F>>());
+    if (cnt) fb_mul_kernel<F, Fr><<<(unsigned)((cnt + 127) / 128), 128, 0, st_main>>>(table.template as<XYZZ<F>>(), d_scalars, (uint32_t)cnt, d_out);
+    G16_CUDA(cudaGetLastError());
+    return G16_OK;
+  }
+  int setup(const uint64_t* alpha_, const uint64_t* beta_, const uint64_t* gamma_, const uint64_t* delta_,
+            const uint64_t* tau_, const uint64_t* g1_, const uint64_t* g2_) override {
+    if (!have_circuit) return fail(G16_ERR_BAD_ARGUMENT, "g16_circuit_load must precede g16_setup");
+    if (!alpha_ || !beta_ || !gamma_ || !delta_ || !tau_ || !g1_ || !g2_) return fail(G16_ERR_BAD_ARGUMENT, "null argument");
+    G16_CUDA(cudaSetDevice(device));
+    const Fr alpha = load_fr(alpha_), beta = load_fr(beta_), gamma = load_fr(gamma_), delta = load_fr(delta_), tau = load_fr(tau_);
+    const A1 g1 = load_a1(g1_);
+    const A2 g2 = load_a2(g2_);
+    if (gamma.is_zero() || delta.is_zero()) return fail(G16_ERR_BAD_ARGUMENT, "gamma/delta must be invertible (UnexpectedIdentity)");
+    const uint64_t n = 1ull << L;
+    const uint32_t nc = num_constraints, ni = num_inputs;
+    const uint64_t nv = nvars();
+    // --- instance_map_with_evaluation (r1cs_to_qap.rs:128-170) on the host ---
+    Fr tn = tau;
+    for (int i = 0; i < L; i++) tn = Fr::sqr(tn);
+    const Fr zt = Fr::sub(tn, Fr::one());                      // evaluate_vanishing_polynomial(t)
+    if (zt.is_zero()) return fail(G16_ERR_BAD_ARGUMENT, "tau lies in the evaluation domain");
+    // Lagrange coefficients u_i = zt * w^i / (n (tau - w^i))   (evaluate_all_lagrange_coefficients)
+    std::vector<Fr> u(n), den(n);
+    {
+      Fr w = Fr::one();
+      for (uint64_t i = 0; i < n; i++) { den[i] = Fr::sub(tau, w); w = Fr::mul(w, dom.omega); }
+      // batch inversion
+      std::vector<Fr> pref(n);
+      Fr acc = Fr::one();
+      for (uint64_t i = 0; i < n; i++) { pref[i] = acc; acc = Fr::mul(acc, den[i]); }
+      Fr ai = Fr::inv(acc);
+      for (uint64_t i = n; i-- > 0;) { Fr t = Fr::mul(ai, pref[i]); ai = Fr::mul(ai, den[i]); den[i] = t; }
+      const Fr zn = Fr::mul(zt, dom.n_inv);
+      w = Fr::one();
+      for (uint64_t i = 0; i < n; i++) { u[i] = Fr::mul(Fr::mul(zn, w), den[i]); w = Fr::mul(w, dom.omega); }
+    }
+    std::vector<Fr> qa(nv, Fr::zero()), qb(nv, Fr::zero()), qc(nv, Fr::zero());
+    for (uint32_t i = 0; i < ni; i++) qa[i] = u[nc + i];                         // r1cs_to_qap.rs:150-155
+    std::vector<Fr>* outs[3] = {&qa, &qb, &qc};
+    for (int m = 0; m < 3; m++)
+      for (uint32_t i = 0; i < nc; i++)
+        for (uint32_t e = h_rp[m][i]; e < h_rp[m][i + 1]; e++) {
+          Fr& dst = (*outs[m])[h_col[m][e]];
+          dst = Fr::add(dst, Fr::mul(u[i], h_val[m][e]));                          // r1cs_to_qap.rs:157-167
+        }
+    const Fr gi = Fr::inv(gamma), di = Fr::inv(delta);
+    std::vector<Fr> gabc(ni), lq(num_witness), hs(n - 1);
+    for (uint64_t i = 0; i < nv; i++) {
+      const Fr t = Fr::add(Fr::add(Fr::mul(beta, qa[i]), Fr::mul(alpha, qb[i])), qc[i]);
+      if (i < ni) gabc[i] = Fr::mul(t, gi);                                        // generator.rs:113-117
+      else lq[i - ni] = Fr::mul(t, di);                                            // generator.rs:119-123
+    }
+    {
+      Fr p = Fr::mul(zt, di);                                                      // h_query_scalars, r1cs_to_qap.rs:237-247
+      for (uint64_t i = 0; i + 1 < n; i++) { hs[i] = p; p = Fr::mul(p, tau); }
+    }
+    // --- fixed-base batch multiplications on the GPU (generator.rs:129-183) ---
+    rank = 0; world = 1;
+    DevBuf d_s, tab1, tab2;
+    const uint64_t maxs = std::max<uint64_t>(nv, n);
+    G16_CUDA(d_s.reserve(maxs * 32));
+    int rc;
+    auto up = [&](const std::vector<Fr>& v) -> cudaError_t {
+      return v.empty() ? cudaSuccess : cudaMemcpyAsync(d_s.p, v.data(), v.size() * 32, cudaMemcpyHostToDevice, st_main);
+    };
+    G16_CUDA(full_a.reserve(nv * sizeof(A1))); G16_CUDA(full_b1.reserve(nv * sizeof(A1))); G16_CUDA(full_b2.reserve(nv * sizeof(A2)));
+    G16_CUDA(d_gamma_abc.reserve((size_t)ni * sizeof(A1)));
+    shard(q[M_H], n - 1); shard(q[M_L], num_witness); shard(q[M_A], nv - 1); shard(q[M_B1], nv - 1); shard(q[M_B2], nv - 1);
+    G16_CUDA(q[M_H].bases.reserve((n - 1) * sizeof(A1) + 16)); G16_CUDA(q[M_L].bases.reserve((size_t)num_witness * sizeof(A1) + 16));
+    // a_query / b_g1_query / b_g2_query
+    G16_CUDA(up(qa)); if ((rc = batch_mul<Fq>(g1, d_s.template as<Fr>(), nv, full_a.template as<A1>(), tab1))) return rc;
+    G16_CUDA(cudaStreamSynchronize(st_main));
+    G16_CUDA(up(qb)); if ((rc = batch_mul<Fq>(g1, d_s.template as<Fr>(), nv, full_b1.template as<A1>(), tab1))) return rc;
+    if ((rc = batch_mul<Fq2>(g2, d_s.template as<Fr>(), nv, full_b2.template as<A2>(), tab2))) return rc;
+    G16_CUDA(cudaStreamSynchronize(st_main));
+    G16_CUDA(up(hs)); if ((rc = batch_mul<Fq>(g1, d_s.template as<Fr>(), n - 1, q[M_H].bases.template as<A1>(), tab1))) return rc;
+    G16_CUDA(cudaStreamSynchronize(st_main));
+    G16_CUDA(up(lq)); if ((rc = batch_mul<Fq>(g1, d_s.template as<Fr>(), num_witness, q[M_L].bases.template as<A1>(), tab1))) return rc;
+    G16_CUDA(cudaStreamSynchronize(st_main));
+    G16_CUDA(up(gabc)); if ((rc = batch_mul<Fq>(g1, d_s.template as<Fr>(), ni, d_gamma_abc.template as<A1>(), tab1))) return rc;
+    G16_CUDA(cudaStreamSynchronize(st_main));
+    // MSM views: query[1..]
+    auto view = [&](Query& x, DevBuf& full, size_t esz) -> int {
+      G16_CUDA(x.bases.reserve((nv - 1) * esz + 16));
+      if (nv > 1) G16_CUDA(cudaMemcpyAsync(x.bases.p, (char*)full.p + esz, (nv - 1) * esz, cudaMemcpyDeviceToDevice, st_main));
+      return G16_OK;
+    };
+    if ((rc = view(q[M_A], full_a, sizeof(A1)))) return rc;
+    if ((rc = view(q[M_B1], full_b1, sizeof(A1)))) return rc;
+    if ((rc = view(q[M_B2], full_b2, sizeof(A2)))) return rc;
+    for (int m = 0; m < 5; m++) {
+      const uint64_t cnt = q[m].hi - q[m].lo;
+      G16_CUDA(q[m].mask.reserve(cnt + 16));
+      if (!cnt) continue;
+      if (m == M_B2) msm_inf_mask<Fq2><<<(unsigned)((cnt + 255) / 256), 256, 0, st_main>>>(q[m].bases.template as<A2>(), (uint32_t)cnt, q[m].mask.template as<uint8_t>());
+      else msm_inf_mask<Fq><<<(unsigned)((cnt + 255) / 256), 256, 0, st_main>>>(q[m].bases.template as<A1>(), (uint32_t)cnt, q[m].mask.template as<uint8_t>());
+    }
+    G16_CUDA(cudaGetLastError());
+    G16_CUDA(cudaMemcpyAsync(&a0, full_a.p, sizeof(A1), cudaMemcpyDeviceToHost, st_main));
+    G16_CUDA(cudaMemcpyAsync(&b1_0, full_b1.p, sizeof(A1), cudaMemcpyDeviceToHost, st_main));
+    G16_CUDA(cudaMemcpyAsync(&b2_0, full_b2.p, sizeof(A2), cudaMemcpyDeviceToHost, st_main));
+    G16_CUDA(cudaStreamSynchronize(st_main));
+    // single points on the host (generator.rs:147-151,182)
+    uint32_t k[8];
+    auto mul1 = [&](const Fr& s) { fr_to_canon(s, k); return P1::from_affine(g1).mul_u32(k, 8).to_affine(); };
+    auto mul2 = [&](const Fr& s) { fr_to_canon(s, k); return P2::from_affine(g2).mul_u32(k, 8).to_affine(); };
+    alpha_g1 = mul1(alpha); beta_g1 = mul1(beta); delta_g1 = mul1(delta);
+    beta_g2 = mul2(beta); gamma_g2 = mul2(gamma); delta_g2 = mul2(delta);
+    d_s.release(); tab1.release(); tab2.release();
+    have_pk = true;
+    from_setup = true;
+    return G16_OK;
+  }
+  int pk_export(const g16_pk_export_desc* o) override {
+    if (!have_pk || !from_setup) return fail(G16_ERR_BAD_ARGUMENT, "g16_pk_export needs a key produced by g16_setup");
+    if (!o) return fail(G16_ERR_BAD_ARGUMENT, "null");
+    G16_CUDA(cudaSetDevice(device));
+    const uint64_t nv = nvars(), n = 1ull << L;
+    if (o->a_query) G16_CUDA(cudaMemcpy(o->a_query, full_a.p, nv * sizeof(A1), cudaMemcpyDeviceToHost));
+    if (o->b_g1_query) G16_CUDA(cudaMemcpy(o->b_g1_query, full_b1.p, nv * sizeof(A1), cudaMemcpyDeviceToHost));
+    if (o->b_g2_query) G16_CUDA(cudaMemcpy(o->b_g2_query, full_b2.p, nv * sizeof(A2), cudaMemcpyDeviceToHost));
+    if (o->h_query && n > 1) G16_CUDA(cudaMemcpy(o->h_query, q[M_H].bases.p, (n - 1) * sizeof(A1), cudaMemcpyDeviceToHost));
+    if (o->l_query && num_witness) G16_CUDA(cudaMemcpy(o->l_query, q[M_L].bases.p, (size_t)num_witness * sizeof(A1), cudaMemcpyDeviceToHost));
+    if (o->gamma_abc_g1) G16_CUDA(cudaMemcpy(o->gamma_abc_g1, d_gamma_abc.p, (size_t)num_inputs * sizeof(A1), cudaMemcpyDeviceToHost));
+    if (o->alpha_g1) store_a1(o->alpha_g1, alpha_g1);
+    if (o->beta_g1) store_a1(o->beta_g1, beta_g1);
+    if (o->delta_g1) store_a1(o->delta_g1, delta_g1);
+    if (o->beta_g2) store_a2(o->beta_g2, beta_g2);
+    if (o->gamma_g2) store_a2(o->gamma_g2, gamma_g2);
+    if (o->delta_g2) store_a2(o->delta_g2, delta_g2);
+    return G16_OK;
+  }
+
+  // ---- proving ----
+  // enqueue: upload z, row evaluation, witness map on st_main
+  int enqueue_witness_map(const uint64_t* z, uint32_t flags) {
+    const uint64_t nv = nvars();
+    tm.h2d_bytes = 0;
+    G16_CUDA(cudaEventRecord(ev_start, st_main));
+    if (flags & G16_ASSIGNMENT_ON_DEVICE) {
+      G16_CUDA(cudaMemcpyAsync(d_z.p, z, nv * 32, cudaMemcpyDeviceToDevice, st_main));
+    } else {
+      G16_CUDA(cudaMemcpyAsync(d_z.p, z, nv * 32, cudaMemcpyHostToDevice, st_main));
+      tm.h2d_bytes = nv * 32;
+    }
+    G16_CUDA(cudaEventRecord(ev_z, st_main));
+    const uint32_t n = 1u << L;
+    CsrDev cs[3];
+    for (int m = 0; m < 3; m++) cs[m] = CsrDev{csr_rp[m].template as<uint32_t>(), csr_col[m].template as<uint32_t>(), csr_val[m].p};
+    r1cs_matvec_kernel<Fr><<<(n + 255) / 256, 256, 0, st_main>>>(cs[0], cs[1], cs[2], d_z.template as<Fr>(), num_constraints, num_inputs, n,
+                                                                 d_a.template as<Fr>(), d_b.template as<Fr>(), d_c.template as<Fr>());
+    ntt_launches++;
+    witness_map_device();
+    G16_CUDA(cudaGetLastError());
+    G16_CUDA(cudaEventRecord(ev_h, st_main));
+    return G16_OK;
+  }
+  int witness_map(const uint64_t* z, uint32_t flags, uint64_t* h) override {
+    if (!have_circuit) return fail(G16_ERR_BAD_ARGUMENT, "no circuit resident");
+    if (!z || !h) return fail(G16_ERR_BAD_ARGUMENT, "null buffer");
+    G16_CUDA(cudaSetDevice(device));
+    int rc = enqueue_witness_map(z, flags);
+    if (rc) return rc;
+    G16_CUDA(cudaMemcpyAsync(h, d_h.p, (size_t)32 << L, cudaMemcpyDeviceToHost, st_main));
+    G16_CUDA(cudaStreamSynchronize(st_main));
+    return G16_OK;
+  }
+
+  struct Partials { P1 h, l, a, b1; P2 b2; };
+  int run_msms(const uint64_t* r, const uint64_t* z, uint32_t flags, Partials& out) {
+    if (!have_circuit || !have_pk) return fail(G16_ERR_BAD_ARGUMENT, "circuit and proving key must be resident");
+    if (!r || !z) return fail(G16_ERR_BAD_ARGUMENT, "null buffer");
+    G16_CUDA(cudaSetDevice(device));
+    const unsigned long long l0 = ctr.launches + ntt_launches;
+    const bool serial = (flags & G16_SERIAL_MSMS) != 0;
+    const bool r_zero = load_fr(r).is_zero();
+    int rc = enqueue_witness_map(z, flags);
+    if (rc) return rc;
+    const uint32_t* zs = d_z.template as<uint32_t>();
+    const uint32_t* hs = d_h.template as<uint32_t>();
+    // scalar sources (prover.rs:63-85): H <- h ; L <- aux ; A, B1, B2 <- input[1..] ++ aux
+    const uint32_t* src[5] = {hs, zs + (size_t)num_inputs * 8, zs + 8, zs + 8, zs + 8};
+    MsmGeom geom[5];
+    bool run[5];
+    for (int m = 0; m < 5; m++) {
+      const uint64_t cnt = q[m].hi - q[m].lo;
+      geom[m] = msm_geom(cnt, FR_BITS);
+      run[m] = cnt > 0 && !(m == M_B1 && r_zero);                        // prover.rs:98: B in G1 skipped when r == 0
+      tm.msm_pairs[m] = run[m] ? cnt : 0;
+    }
+    const int order[5] = {M_L, M_A, M_B1, M_B2, M_H};                    // H last: it waits for the witness map
+    for (int oi = 0; oi < 5; oi++) {
+      const int m = order[oi];
+      cudaStream_t st = serial ? st_main : st_msm[m];
+      if (!serial) G16_CUDA(cudaStreamWaitEvent(st, m == M_H ? ev_h : ev_z, 0));
+      G16_CUDA(cudaEventRecord(ev_m0[m], st));
+      if (run[m]) {
+        const uint32_t* sc = src[m] + q[m].lo * 8;
+        cudaError_t e;
+        if (m == M_B2) e = msm_enqueue<Fq2, Fr>(st, ws2, geom[m], q[m].bases.template as<A2>(), q[m].mask.template as<uint8_t>(), sc, true, &ctr, ev_a0[m], ev_a1[m]);
+        else e = msm_enqueue<Fq, Fr>(st, ws1[m], geom[m], q[m].bases.template as<A1>(), q[m].mask.template as<uint8_t>(), sc, true, &ctr, ev_a0[m], ev_a1[m]);
+        if (e != cudaSuccess) return fail(G16_ERR_CUDA, std::string("msm_enqueue: ") + cudaGetErrorString(e));
+      }
+      G16_CUDA(cudaEventRecord(ev_m1[m], st));
+    }
+    G16_CUDA(cudaStreamSynchronize(st_main));
+    if (!serial) for (int m = 0; m < 5; m++) G16_CUDA(cudaStreamSynchronize(st_msm[m]));
+    auto t0 = std::chrono::steady_clock::now();
+    out.h = run[M_H] ? msm_finish<Fq>(ws1[M_H], geom[M_H]) : P1::inf();
+    out.l = run[M_L] ? msm_finish<Fq>(ws1[M_L], geom[M_L]) : P1::inf();
+    out.a = run[M_A] ? msm_finish<Fq>(ws1[M_A], geom[M_A]) : P1::inf();
+    out.b1 = run[M_B1] ? msm_finish<Fq>(ws1[M_B1], geom[M_B1]) : P1::inf();
+    out.b2 = run[M_B2] ? msm_finish<Fq2>(ws2, geom[M_B2]) : P2::inf();
+    auto t1 = std::chrono::steady_clock::now();
+    tm.host_finish_ms = std::chrono::duration<float, std::milli>(t1 - t0).count();
+    // timings
+    float ms = 0, tot = 0;
+    cudaEventElapsedTime(&tm.h2d_ms, ev_start, ev_z);
+    cudaEventElapsedTime(&tm.witness_map_ms, ev_z, ev_h);
+    cudaEventElapsedTime(&tot, ev_start, ev_h);
+    for (int m = 0; m < 5; m++) {
+      cudaEventElapsedTime(&tm.msm_ms[m], ev_m0[m], ev_m1[m]);
+      tm.msm_accum_ms[m] = 0;
+      if (run[m]) cudaEventElapsedTime(&tm.msm_accum_ms[m], ev_a0[m], ev_a1[m]);
+      cudaEventElapsedTime(&ms, ev_start, ev_m1[m]);
+      if (ms > tot) tot = ms;
+    }
+    tm.total_ms = tot;
+    tm.launches = ctr.launches + ntt_launches - l0;
+    tm.d2h_bytes = 0;
+    for (int m = 0; m < 5; m++) if (run[m]) tm.d2h_bytes += (uint64_t)geom[m].W * (m == M_B2 ? sizeof(P2) : sizeof(P1));
+    return G16_OK;
+  }
+  void store_partials(uint64_t* p, const Partials& x) {
+    store_a1(p, x.h.to_affine());
+    store_a1(p + 2 * NQ64, x.l.to_affine());
+    store_a1(p + 4 * NQ64, x.a.to_affine());
+    store_a1(p + 6 * NQ64, x.b1.to_affine());
+    store_a2(p + 8 * NQ64, x.b2.to_affine());
+  }
+  int prove_partial(const uint64_t* r, const uint64_t* z, uint32_t flags, uint64_t* partial) override {
+    if (!partial) return fail(G16_ERR_BAD_ARGUMENT, "null buffer");
+    Partials x;
+    int rc = run_msms(r, z, flags, x);
+    if (rc) return rc;
+    store_partials(partial, x);
+    return G16_OK;
+  }
+  // prover.rs:76-131 on the host, from the five MSM sums
+  int assemble(const Fr& r, const Fr& s, const Partials& x, uint64_t* proof) {
+    uint32_t rk[8], sk[8], rsk[8];
+    fr_to_canon(r, rk);
+    fr_to_canon(s, sk);
+    fr_to_canon(Fr::mul(r, s), rsk);
+    const P1 d1 = P1::from_affine(delta_g1);
+    P1 r_s_delta_g1 = d1.mul_u32(rsk, 8);                 // prover.rs:76
+    // g_a = r*delta_g1 + a_query[0] + msm + alpha_g1         prover.rs:90-92,252-270
+    P1 g_a = d1.mul_u32(rk, 8);
+    g_a.madd(a0);
+    g_a.add(x.a);
+    g_a.madd(alpha_g1);
+    P1 s_g_a = g_a.mul_u32(sk, 8);                        // prover.rs:94
+    P1 g1_b = P1::inf();
+    if (!r.is_zero()) {                                   // prover.rs:98-108
+      g1_b = d1.mul_u32(sk, 8);
+      g1_b.madd(b1_0);
+      g1_b.add(x.b1);
+      g1_b.madd(beta_g1);
+    }
+    P2 g2_b = P2::from_affine(delta_g2).mul_u32(sk, 8);   // prover.rs:112-113
+    g2_b.madd(b2_0);
+    g2_b.add(x.b2);
+    g2_b.madd(beta_g2);
+    P1 r_g1_b = g1_b.mul_u32(rk, 8);                      // prover.rs:114
+    P1 g_c = s_g_a;                                       // prover.rs:119-124
+    g_c.add(r_g1_b);
+    r_s_delta_g1.negate();
+    g_c.add(r_s_delta_g1);
+    g_c.add(x.l);
+    g_c.add(x.h);
+    store_a1(proof, g_a.to_affine());                     // prover.rs:127-131
+    store_a2(proof + 2 * NQ64, g2_b.to_affine());
+    store_a1(proof + 6 * NQ64, g_c.to_affine());
+    return G16_OK;
+  }
+  int prove(const uint64_t* r, const uint64_t* s, const uint64_t* z, uint32_t flags, uint64_t* proof) override {
+    if (!s || !proof) return fail(G16_ERR_BAD_ARGUMENT, "null buffer");
+    if (world != 1) return fail(G16_ERR_BAD_ARGUMENT, "key is sharded: use g16_prove_partial + g16_prove_assemble");
+    Partials x;
+    int rc = run_msms(r, z, flags, x);
+    if (rc) return rc;
+    auto t0 = std::chrono::steady_clock::now();
+    rc = assemble(load_fr(r), load_fr(s), x, proof);
+    tm.host_finish_ms += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    tm.d2h_bytes += 8 * NQ64 * 8;
+    return rc;
+  }
+  int prove_assemble(const uint64_t* r, const uint64_t* s, const uint64_t* partials, uint32_t nparts, uint64_t* proof) override {
+    if (!have_pk) return fail(G16_ERR_BAD_ARGUMENT, "no proving key resident");
+    if (!r || !s || !partials || !proof || nparts == 0) return fail(G16_ERR_BAD_ARGUMENT, "null buffer");
+    Partials x{P1::inf(), P1::inf(), P1::inf(), P1::inf(), P2::inf()};
+    const int pl = partial_limbs();
+    for (uint32_t i = 0; i < nparts; i++) {   // fixed rank order; the sum is order-independent anyway
+      const uint64_t* p = partials + (size_t)i * pl;
+      x.h.madd(load_a1(p));
+      x.l.madd(load_a1(p + 2 * NQ64));
+      x.a.madd(load_a1(p + 4 * NQ64));
+      x.b1.madd(load_a1(p + 6 * NQ64));
+      x.b2.madd(load_a2(p + 8 * NQ64));
+    }
+    return assemble(load_fr(r), load_fr(s), x, proof);
+  }
+};
+
+template <class CP>
+IEngine* make_engine(int device, int* rc) {
+  auto* e = new Engine<CP>();
+  *rc = e->init(device);
+  if (*rc) { delete e; return nullptr; }
+  return e;
+}
+
+}  // namespace g16

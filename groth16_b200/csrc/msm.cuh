@@ -1,0 +1,436 @@
+// msm.cuh -- variable-base multi-scalar multiplication on sm_100a (Pippenger, signed digits, sort-by-bucket).
+//
+// Replaces ark-ec 0.5.0 `VariableBaseMSM::msm_bigint` as called at /root/reference/src/prover.rs:66 (H query),
+// :74 (L query) and :262 (A, B-in-G1, B-in-G2 via calculate_coeff).  The group element returned is identical to
+// the reference's (EC addition is exactly associative/commutative), whatever the window size or summation order.
+//
+// Pipeline (all on one stream, no host synchronisation until the W window sums are read back):
+//   1. msm_digits<COUNT>   scalar -> W signed c-bit digits; histogram of (window, |digit|) keys (warp-aggregated atomics)
+//   2. msm_scan            exclusive prefix sum of the histogram -> bucket offsets
+//   3. msm_digits<SCATTER> counting-sort scatter: sorted (base index | sign) and key per entry
+//   4. msm_accum_l0        load-balanced segmented reduction: every thread owns K0 consecutive sorted entries,
+//                          mixed-adds them (XYZZ += affine, gathered from the resident base array), writes buckets
+//                          that are complete inside its chunk and emits <= 2 boundary partials
+//   5. msm_accum_ln        the same reduction over the partial list, level by level, until one thread remains
+//   6. msm_bucket_reduce   per (window, segment of L buckets): running-sum trick + (segment offset) * sum
+//   7. msm_sum_groups      tree-sum of the segment results -> one point per window
+//   host: Horner over windows (c doublings each), prover.rs semantics preserved.
+// Skewed scalar distributions (boolean witnesses, the reference's DummyCircuit whose witness is constant,
+// benches/bench.rs:43-54) cost the same as uniform ones: work is split by sorted position, not by bucket.
+#pragma once
+#include <cuda_runtime.h>
+#include "ec.cuh"
+
+namespace g16 {
+
+static constexpr uint32_t MSM_INVALID = 0xffffffffu;
+
+struct MsmGeom {
+  uint32_t n;        // number of (scalar, base) pairs
+  int c;             // window bits
+  int W;             // number of windows
+  uint32_t B;        // buckets per window = 2^(c-1)  (digit magnitudes 1..B)
+  uint32_t nkeys;    // W * B
+  uint64_t max_entries;  // n * W
+};
+
+inline int msm_pick_c(uint64_t n) {
+  int lg = 0;
+  while ((1ull << lg) < n) lg++;
+  int c = lg - 4;
+  if (c < 3) c = 3;
+  if (c > 16) c = 16;
+  return c;
+}
+inline MsmGeom msm_geom(uint64_t n, int scalar_bits, int c_override = 0) {
+  MsmGeom g;
+  g.n = (uint32_t)n;
+  g.c = c_override > 0 ? c_override : msm_pick_c(n);
+  g.W = (scalar_bits + 1 + g.c - 1) / g.c;   // +1: room for the top signed-digit carry
+  g.B = 1u << (g.c - 1);
+  g.nkeys = (uint32_t)g.W * g.B;
+  g.max_entries = (uint64_t)n * g.W;
+  return g;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 1/3. digit extraction + histogram / scatter
+// ------------------------------------------------------------------------------------------------
+// Signed-digit recoding of a canonical scalar k < 2^bits:  k = sum_w d_w 2^(c w), d_w in [-2^(c-1), 2^(c-1)].
+template <class FrF, bool SCATTER>
+__global__ void __launch_bounds__(256) msm_digits(const uint32_t* __restrict__ scalars, int scalars_mont,
+                                                  const uint8_t* __restrict__ skip, MsmGeom g,
+                                                  uint32_t* __restrict__ counters,  // COUNT: histogram; SCATTER: cursors
+                                                  uint32_t* __restrict__ sidx, uint32_t* __restrict__ skey) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31;
+  bool live = i < g.n;
+  FrF s = FrF::zero();
+  if (live) {
+    const uint4* p = reinterpret_cast<const uint4*>(scalars) + (size_t)i * 2;
+    uint4 lo = __ldg(p), hi = __ldg(p + 1);
+    s.v[0] = lo.x; s.v[1] = lo.y; s.v[2] = lo.z; s.v[3] = lo.w;
+    s.v[4] = hi.x; s.v[5] = hi.y; s.v[6] = hi.z; s.v[7] = hi.w;
+    if (skip && skip[i]) live = false;
+  }
+  if (scalars_mont) s = FrF::from_mont(s);   // `into_bigint`, prover.rs:64,71,82
+  uint32_t carry = 0;
+  for (int w = 0; w < g.W; w++) {
+    // c <= 16 bits starting at bit w*c
+    const int bit = w * g.c;
+    const int limb = bit >> 5, sh = bit & 31;
+    uint32_t raw = 0;
+    if (limb < 8) {
+      uint64_t two = s.v[limb];
+      if (limb + 1 < 8) two |= (uint64_t)s.v[limb + 1] << 32;
+      raw = (uint32_t)(two >> sh) & ((1u << g.c) - 1);
+    }
+    raw += carry;
+    uint32_t neg = 0;
+    carry = 0;
+    if (raw > g.B) { raw = (1u << g.c) - raw; neg = 1; carry = 1; }
+    const bool emit = live && raw != 0;
+    const uint32_t key = emit ? (uint32_t)w * g.B + (raw - 1) : MSM_INVALID;
+    // warp-aggregated atomic: one atomicAdd per distinct key in the warp
+    const uint32_t peers = __match_any_sync(0xffffffffu, key);
+    if (emit) {
+      const uint32_t rank = __popc(peers & ((1u << lane) - 1));
+      const int leader = __ffs(peers) - 1;
+      uint32_t base = 0;
+      if ((int)lane == leader) base = atomicAdd(&counters[key], (uint32_t)__popc(peers));
+      base = __shfl_sync(peers, base, leader);
+      if (SCATTER) {
+        const uint32_t pos = base + rank;
+        sidx[pos] = i | (neg << 31);
+        skey[pos] = key;
+      }
+    }
+  }
+}
+
+// 2. exclusive scan (single block; nkeys <= a few million).  offsets[nkeys] = total.  Also copies to cursors.
+// `hist` and `cursors` may alias (the histogram is turned into the scatter cursors in place).
+static __global__ void __launch_bounds__(1024) msm_scan(const uint32_t* hist, uint32_t nkeys, uint32_t* offsets,
+                                                 uint32_t* cursors) {
+  __shared__ uint32_t part[1024];
+  const uint32_t t = threadIdx.x;
+  const uint32_t per = (nkeys + 1023) / 1024;
+  const uint32_t lo = min(t * per, nkeys), hi = min(lo + per, nkeys);
+  uint32_t s = 0;
+  for (uint32_t j = lo; j < hi; j++) s += hist[j];
+  part[t] = s;
+  __syncthreads();
+  // Hillis-Steele inclusive scan over 1024 partials
+  for (uint32_t d = 1; d < 1024; d <<= 1) {
+    uint32_t v = (t >= d) ? part[t - d] : 0;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  uint32_t run = part[t] - s;
+  for (uint32_t j = lo; j < hi; j++) {
+    const uint32_t h = hist[j];
+    offsets[j] = run;
+    cursors[j] = run;
+    run += h;
+  }
+  if (t == 1023) offsets[nkeys] = part[1023];
+}
+
+// ------------------------------------------------------------------------------------------------
+// 4/5. load-balanced segmented bucket accumulation
+// ------------------------------------------------------------------------------------------------
+template <class F>
+__device__ __forceinline__ void msm_flush(uint32_t key, const XYZZ<F>& acc, bool head, bool tail, uint64_t t,
+                                          XYZZ<F>* __restrict__ buckets, uint32_t* __restrict__ okeys,
+                                          XYZZ<F>* __restrict__ opts) {
+  if (!head && !tail) {
+    buckets[key] = acc;   // the whole bucket was summed here: written exactly once, no atomics
+  } else {
+    const uint64_t slot = 2 * t + (head ? 0 : 1);
+    okeys[slot] = key;
+    opts[slot] = acc;
+  }
+}
+
+template <class F>
+__device__ __forceinline__ Affine<F> load_affine(const Affine<F>* __restrict__ bases, uint32_t idx) {
+  Affine<F> p;
+  constexpr int NV = sizeof(Affine<F>) / 16;
+  const uint4* src = reinterpret_cast<const uint4*>(bases + idx);
+  uint4* dst = reinterpret_cast<uint4*>(&p);
+#pragma unroll
+  for (int j = 0; j < NV; j++) dst[j] = __ldg(src + j);
+  return p;
+}
+
+template <class F, int K0>
+__global__ void __launch_bounds__(128) msm_accum_l0(const Affine<F>* __restrict__ bases,
+                                                    const uint32_t* __restrict__ sidx,
+                                                    const uint32_t* __restrict__ skey,
+                                                    const uint32_t* __restrict__ total_ptr,
+                                                    XYZZ<F>* __restrict__ buckets, uint32_t* __restrict__ okeys,
+                                                    XYZZ<F>* __restrict__ opts) {
+  const uint32_t M = *total_ptr;
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t begin = t * K0;
+  if (begin >= M) return;
+  const uint32_t end = (uint32_t)min((uint64_t)M, begin + K0);
+  const uint32_t prev = begin > 0 ? skey[begin - 1] : MSM_INVALID;
+  const uint32_t next = end < M ? skey[end] : MSM_INVALID;
+  uint32_t cur = skey[begin];
+  bool first_seg = true;
+  XYZZ<F> acc = XYZZ<F>::inf();
+  for (uint32_t e = (uint32_t)begin; e < end; e++) {
+    const uint32_t k = skey[e];
+    if (k != cur) {
+      msm_flush(cur, acc, first_seg && prev == cur, false, t, buckets, okeys, opts);
+      first_seg = false;
+      cur = k;
+      acc = XYZZ<F>::inf();
+    }
+    const uint32_t ix = sidx[e];
+    const Affine<F> p = load_affine(bases, ix & 0x7fffffffu);
+    acc.madd_inline(p, (ix >> 31) != 0);
+  }
+  msm_flush(cur, acc, first_seg && prev == cur, next == cur, t, buckets, okeys, opts);
+}
+
+// keys may contain MSM_INVALID holes (at most one inside a run of equal keys)
+template <class F, int KF>
+__global__ void __launch_bounds__(128) msm_accum_ln(const uint32_t* __restrict__ ikeys,
+                                                    const XYZZ<F>* __restrict__ ipts, uint64_t S,
+                                                    XYZZ<F>* __restrict__ buckets, uint32_t* __restrict__ okeys,
+                                                    XYZZ<F>* __restrict__ opts) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t begin = t * KF;
+  if (begin >= S) return;
+  const uint64_t end = min(S, begin + KF);
+  uint32_t prev = MSM_INVALID, next = MSM_INVALID;
+  if (begin >= 1) prev = ikeys[begin - 1];
+  if (prev == MSM_INVALID && begin >= 2) prev = ikeys[begin - 2];
+  if (end < S) next = ikeys[end];
+  if (next == MSM_INVALID && end + 1 < S) next = ikeys[end + 1];
+  uint32_t cur = MSM_INVALID;
+  bool have = false, first_seg = true;
+  XYZZ<F> acc = XYZZ<F>::inf();
+  for (uint64_t e = begin; e < end; e++) {
+    const uint32_t k = ikeys[e];
+    if (k == MSM_INVALID) continue;
+    if (!have) {
+      have = true;
+      cur = k;
+      acc = ipts[e];
+    } else if (k != cur) {
+      msm_flush(cur, acc, first_seg && prev == cur, false, t, buckets, okeys, opts);
+      first_seg = false;
+      cur = k;
+      acc = ipts[e];
+    } else {
+      acc.add(ipts[e]);
+    }
+  }
+  if (have) msm_flush(cur, acc, first_seg && prev == cur, next == cur, t, buckets, okeys, opts);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 6/7. bucket reduction
+// ------------------------------------------------------------------------------------------------
+// out[w*nseg + seg] = sum_{j<L} (seg*L + j + 1) * bucket[w*B + seg*L + j]
+template <class F>
+__global__ void __launch_bounds__(128) msm_bucket_reduce(const XYZZ<F>* __restrict__ buckets, uint32_t B, uint32_t L,
+                                                         uint32_t total_segs, XYZZ<F>* __restrict__ out) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total_segs) return;
+  const uint32_t nseg = B / L;
+  const uint32_t w = t / nseg, seg = t % nseg;
+  const XYZZ<F>* base = buckets + (size_t)w * B + (size_t)seg * L;
+  XYZZ<F> running = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
+  for (int j = (int)L - 1; j >= 0; j--) {
+    running.add(base[j]);
+    acc.add(running);
+  }
+  if (seg) {
+    uint32_t k = seg * L;
+    acc.add(running.mul_u32(&k, 1));
+  }
+  out[t] = acc;
+}
+
+// out[g] = sum_{j<R} in[g*R + j]   (g < ngroups)
+template <class F>
+__global__ void __launch_bounds__(128) msm_sum_groups(const XYZZ<F>* __restrict__ in, uint32_t R, uint32_t ngroups,
+                                                      XYZZ<F>* __restrict__ out) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ngroups) return;
+  XYZZ<F> acc = in[(size_t)t * R];
+  for (uint32_t j = 1; j < R; j++) acc.add(in[(size_t)t * R + j]);
+  out[t] = acc;
+}
+
+// infinity mask of a base array (x == y == 0), computed once when a query is made resident
+template <class F>
+__global__ void msm_inf_mask(const Affine<F>* __restrict__ bases, uint32_t n, uint8_t* __restrict__ mask) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Affine<F> p = load_affine(bases, i);
+  mask[i] = p.is_inf() ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host driver
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+static constexpr int MSM_K0 = 64;   // sorted entries per thread, level 0
+static constexpr int MSM_KF = 8;    // partial slots per thread, levels >= 1
+static constexpr int MSM_SEG = 16;  // buckets per thread in the bucket reduction
+static constexpr int MSM_GRP = 8;   // fan-in of the window-sum tree
+
+template <class F>
+struct MsmWorkspace {
+  DevBuf counters, offsets, sidx, skey, buckets, pk0, pp0, pk1, pp1, seg0, seg1, winsums;
+  XYZZ<F>* h_winsums = nullptr;  // pinned host staging for the W window sums
+  int h_cap = 0;
+  cudaError_t prepare(const MsmGeom& g) {
+    cudaError_t e;
+    const uint64_t T0 = (g.max_entries + MSM_K0 - 1) / MSM_K0;
+    const uint64_t S1 = 2 * T0;
+    const uint64_t T1 = (S1 + MSM_KF - 1) / MSM_KF;
+    const uint64_t S2 = 2 * T1;
+#define G16_TRY(x) if ((e = (x)) != cudaSuccess) return e
+    G16_TRY(counters.reserve((size_t)(g.nkeys + 1) * 4));
+    G16_TRY(offsets.reserve((size_t)(g.nkeys + 1) * 4));
+    G16_TRY(sidx.reserve(g.max_entries * 4 + 16));
+    G16_TRY(skey.reserve(g.max_entries * 4 + 16));
+    G16_TRY(buckets.reserve((size_t)g.nkeys * sizeof(XYZZ<F>)));
+    G16_TRY(pk0.reserve(S1 * 4 + 16));
+    G16_TRY(pp0.reserve(S1 * sizeof(XYZZ<F>)));
+    G16_TRY(pk1.reserve(S2 * 4 + 16));
+    G16_TRY(pp1.reserve(S2 * sizeof(XYZZ<F>)));
+    const uint32_t L = g.B < (uint32_t)MSM_SEG ? g.B : (uint32_t)MSM_SEG;
+    const uint64_t nsegs = (uint64_t)g.W * (g.B / L);
+    G16_TRY(seg0.reserve(nsegs * sizeof(XYZZ<F>)));
+    G16_TRY(seg1.reserve((nsegs / 2 + g.W) * sizeof(XYZZ<F>)));
+    G16_TRY(winsums.reserve((size_t)g.W * sizeof(XYZZ<F>)));
+    if (h_cap < g.W) {
+      if (h_winsums) cudaFreeHost(h_winsums);
+      G16_TRY(cudaMallocHost(&h_winsums, (size_t)g.W * sizeof(XYZZ<F>)));
+      h_cap = g.W;
+    }
+#undef G16_TRY
+    return cudaSuccess;
+  }
+  void release() {
+    counters.release(); offsets.release(); sidx.release(); skey.release(); buckets.release();
+    pk0.release(); pp0.release(); pk1.release(); pp1.release(); seg0.release(); seg1.release(); winsums.release();
+    if (h_winsums) cudaFreeHost(h_winsums);
+    h_winsums = nullptr;
+    h_cap = 0;
+  }
+};
+
+struct MsmCounters {  // launch bookkeeping for bench.py's gpu_launches
+  unsigned long long launches = 0;
+};
+
+// Enqueue one MSM on `st`.  d_bases / d_scalars / d_skip are device pointers; the W window sums land in
+// ws.h_winsums after the stream is synchronised (msm_finish does the Horner step on the host).
+template <class F, class FrF>
+cudaError_t msm_enqueue(cudaStream_t st, MsmWorkspace<F>& ws, const MsmGeom& g, const Affine<F>* d_bases,
+                        const uint8_t* d_skip, const uint32_t* d_scalars, bool scalars_mont, MsmCounters* ctr,
+                        cudaEvent_t ev_acc0 = nullptr, cudaEvent_t ev_acc1 = nullptr) {
+  cudaError_t e;
+  if (g.n == 0) return cudaSuccess;
+  if ((e = ws.prepare(g)) != cudaSuccess) return e;
+  uint32_t* counters = ws.counters.template as<uint32_t>();
+  uint32_t* offsets = ws.offsets.template as<uint32_t>();
+  uint32_t* sidx = ws.sidx.template as<uint32_t>();
+  uint32_t* skey = ws.skey.template as<uint32_t>();
+  XYZZ<F>* buckets = ws.buckets.template as<XYZZ<F>>();
+  cudaMemsetAsync(counters, 0, (size_t)(g.nkeys + 1) * 4, st);
+  cudaMemsetAsync(buckets, 0, (size_t)g.nkeys * sizeof(XYZZ<F>), st);
+  const uint32_t nb = (g.n + 255) / 256;
+  msm_digits<FrF, false><<<nb, 256, 0, st>>>(d_scalars, scalars_mont ? 1 : 0, d_skip, g, counters, nullptr, nullptr);
+  msm_scan<<<1, 1024, 0, st>>>(counters, g.nkeys, offsets, counters);
+  msm_digits<FrF, true><<<nb, 256, 0, st>>>(d_scalars, scalars_mont ? 1 : 0, d_skip, g, counters, sidx, skey);
+  if (ctr) ctr->launches += 3;
+  // level 0
+  const uint64_t T0 = (g.max_entries + MSM_K0 - 1) / MSM_K0;
+  uint64_t S = 2 * T0;
+  uint32_t* ok = ws.pk0.template as<uint32_t>();
+  XYZZ<F>* op = ws.pp0.template as<XYZZ<F>>();
+  cudaMemsetAsync(ok, 0xff, S * 4, st);
+  if (ev_acc0) cudaEventRecord(ev_acc0, st);
+  msm_accum_l0<F, MSM_K0><<<(unsigned)((T0 + 127) / 128), 128, 0, st>>>(d_bases, sidx, skey, offsets + g.nkeys, buckets, ok, op);
+  if (ev_acc1) cudaEventRecord(ev_acc1, st);
+  if (ctr) ctr->launches += 1;
+  // levels >= 1 (ping-pong between the two partial buffers)
+  bool flip = false;
+  while (true) {
+    const uint64_t T = (S + MSM_KF - 1) / MSM_KF;
+    const uint64_t So = 2 * T;
+    uint32_t* ik = flip ? ws.pk1.template as<uint32_t>() : ws.pk0.template as<uint32_t>();
+    XYZZ<F>* ip = flip ? ws.pp1.template as<XYZZ<F>>() : ws.pp0.template as<XYZZ<F>>();
+    uint32_t* ok2 = flip ? ws.pk0.template as<uint32_t>() : ws.pk1.template as<uint32_t>();
+    XYZZ<F>* op2 = flip ? ws.pp0.template as<XYZZ<F>>() : ws.pp1.template as<XYZZ<F>>();
+    cudaMemsetAsync(ok2, 0xff, So * 4, st);
+    msm_accum_ln<F, MSM_KF><<<(unsigned)((T + 127) / 128), 128, 0, st>>>(ik, ip, S, buckets, ok2, op2);
+    if (ctr) ctr->launches += 1;
+    if (T == 1) break;
+    S = So;
+    flip = !flip;
+  }
+  // bucket reduction
+  const uint32_t L = g.B < (uint32_t)MSM_SEG ? g.B : (uint32_t)MSM_SEG;
+  uint32_t per_win = g.B / L;
+  const uint32_t nsegs = (uint32_t)g.W * per_win;
+  XYZZ<F>* a = ws.seg0.template as<XYZZ<F>>();
+  XYZZ<F>* b = ws.seg1.template as<XYZZ<F>>();
+  msm_bucket_reduce<F><<<(nsegs + 127) / 128, 128, 0, st>>>(buckets, g.B, L, nsegs, a);
+  if (ctr) ctr->launches += 1;
+  while (per_win > 1) {
+    const uint32_t R = per_win < (uint32_t)MSM_GRP ? per_win : (uint32_t)MSM_GRP;   // per_win is a power of two
+    const uint32_t ng = (uint32_t)g.W * (per_win / R);
+    msm_sum_groups<F><<<(ng + 127) / 128, 128, 0, st>>>(a, R, ng, b);
+    if (ctr) ctr->launches += 1;
+    XYZZ<F>* t = a; a = b; b = t;
+    per_win /= R;
+  }
+  e = cudaMemcpyAsync(ws.h_winsums, a, (size_t)g.W * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, st);
+  if (e != cudaSuccess) return e;
+  return cudaGetLastError();
+}
+
+// Host Horner over the window sums (stream must be synchronised): sum_w 2^(c w) S_w.
+template <class F>
+XYZZ<F> msm_finish(const MsmWorkspace<F>& ws, const MsmGeom& g) {
+  XYZZ<F> acc = XYZZ<F>::inf();
+  if (g.n == 0) return acc;
+  for (int w = g.W - 1; w >= 0; w--) {
+    for (int k = 0; k < g.c; k++) acc.dbl_inplace();
+    acc.add(ws.h_winsums[w]);
+  }
+  return acc;
+}
+
+}  // namespace g16

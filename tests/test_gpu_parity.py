@@ -1,0 +1,235 @@
+"""GPU parity tests (run on a B200 with `pytest -m gpu`): every C-ABI entry point against the CPU oracle.
+
+Bar: bit-exact (integer arithmetic throughout).  Reference behaviour cited per test."""
+import numpy as np
+import pytest
+
+import pyref as P
+from groth16_b200 import CurveCodec, Groth16, PolynomialDegreeTooLarge, get_curve
+from util import ALL_CURVES, matrices_from_r1cs, pk_from_abi, pk_to_abi, proof_from_abi, toxic
+
+pytestmark = pytest.mark.gpu
+
+_ENGINES = {}
+
+
+def engine(name) -> Groth16:
+    if name not in _ENGINES:
+        _ENGINES[name] = Groth16(name, 0)
+    return _ENGINES[name]
+
+
+@pytest.mark.parametrize("curve", ALL_CURVES)
+@pytest.mark.parametrize("log_n", [0, 1, 3, 6, 10, 11, 13])
+def test_ntt_matches_oracle(curve, log_n):
+    """ark-poly fft/ifft/coset (r1cs_to_qap.rs:201-207,232): natural order in/out, omega = two_adic_root^(2^(s-log n))."""
+    c = P.CURVES[curve]
+    g = engine(curve)
+    cd = g.codec
+    rng = P.Rng(100 + log_n)
+    n = 1 << log_n
+    vals = [rng.fr(c.r) for _ in range(n)]
+    dom = P.Domain(c, n)
+    enc = cd.fr.enc(vals)
+    assert cd.fr.dec(g.ntt_log(log_n, enc)) == dom.fft(vals)
+    assert cd.fr.dec(g.ntt_log(log_n, enc, inverse=True)) == dom.ifft(vals)
+    assert cd.fr.dec(g.ntt_log(log_n, enc, coset=True)) == dom.fft(vals, offset=c.fr_gen)
+    assert cd.fr.dec(g.ntt_log(log_n, enc, inverse=True, coset=True)) == dom.ifft(vals, offset=c.fr_gen)
+
+
+def test_ntt_degree_too_large():
+    """D::new(..) -> None -> PolynomialDegreeTooLarge (r1cs_to_qap.rs:178-179): BN254 two-adicity is 28."""
+    g = engine("bn254")
+    with pytest.raises(PolynomialDegreeTooLarge):
+        g.ntt_log(29, np.zeros((1, 4), dtype=np.uint64))
+
+
+@pytest.mark.parametrize("curve", ALL_CURVES)
+@pytest.mark.parametrize("log_n", [3, 11])
+def test_witness_map_evals(curve, log_n):
+    """r1cs_to_qap.rs:201-234 on arbitrary evaluation vectors."""
+    c = P.CURVES[curve]
+    g = engine(curve)
+    cd = g.codec
+    rng = P.Rng(7 + log_n)
+    n = 1 << log_n
+    a, b, cc = ([rng.fr(c.r) for _ in range(n)] for _ in range(3))
+    dom = P.Domain(c, n)
+    want = P.witness_map_from_evals(dom, a, b, cc)
+    got = cd.fr.dec(g.witness_map_from_evals(cd.fr.enc(a), cd.fr.enc(b), cd.fr.enc(cc)))
+    assert got == want
+
+
+def _edge_scalars(c, rng, n):
+    sc = [rng.fr(c.r) for _ in range(n)]
+    special = [0, 1, 2, c.r - 1, c.r - 2, (1 << 128), (1 << 16) - 1, 1 << 15, (1 << 15) + 1]
+    for i, v in enumerate(special):
+        if i < n:
+            sc[i] = v % c.r
+    return sc
+
+
+@pytest.mark.parametrize("curve", ALL_CURVES)
+@pytest.mark.parametrize("n", [0, 1, 2, 17, 300])
+def test_msm_g1(curve, n):
+    """VariableBaseMSM::msm_bigint (prover.rs:66,74,262) vs double-and-add; zero/one/r-1 scalars, identity bases,
+    repeated bases (P+P) and inverse pairs (P-P)."""
+    c = P.CURVES[curve]
+    cx = P.ctx(c)
+    g = engine(curve)
+    cd = g.codec
+    rng = P.Rng(31 + n)
+    gen = cx.g1_gen()
+    bases = [cx.G1.mul(gen, rng.fr(c.r)) for _ in range(n)]
+    if n >= 17:
+        bases[3] = None
+        bases[5] = bases[4]
+        bases[7] = cx.G1.neg(bases[6])
+    sc = _edge_scalars(c, rng, n)
+    if n >= 17:
+        sc[5] = sc[4]
+        sc[7] = sc[6]
+    want = cx.G1.msm_naive(bases, sc)
+    got = cd.dec_proj_g1(g.msm_g1(cd.enc_g1(bases) if n else np.zeros((0, 2 * g.nq), dtype=np.uint64),
+                                  cd.fr.bigint(sc) if n else np.zeros((0, 4), dtype=np.uint64)))
+    assert got == want
+
+
+@pytest.mark.parametrize("curve", ALL_CURVES)
+@pytest.mark.parametrize("n", [1, 40])
+def test_msm_g2(curve, n):
+    c = P.CURVES[curve]
+    cx = P.ctx(c)
+    g = engine(curve)
+    cd = g.codec
+    rng = P.Rng(77 + n)
+    gen = cx.g2_gen()
+    bases = [cx.G2.mul(gen, rng.fr(c.r)) for _ in range(n)]
+    sc = _edge_scalars(c, rng, n)
+    if n >= 17:
+        bases[3] = None
+        bases[5] = bases[4]
+        sc[5] = sc[4]
+    want = cx.G2.msm_naive(bases, sc)
+    got = cd.dec_proj_g2(g.msm_g2(cd.enc_g2(bases), cd.fr.bigint(sc)))
+    assert got == want
+
+
+def test_msm_truncates_like_ark():
+    """msm_bigint uses min(bases.len(), scalars.len()) (relied upon at prover.rs:66)."""
+    c = P.CURVES["bn254"]
+    cx = P.ctx(c)
+    g = engine("bn254")
+    cd = g.codec
+    rng = P.Rng(5)
+    bases = [cx.G1.mul(cx.g1_gen(), rng.fr(c.r)) for _ in range(7)]
+    sc = [rng.fr(c.r) for _ in range(8)]
+    assert cd.dec_proj_g1(g.msm_g1(cd.enc_g1(bases), cd.fr.bigint(sc))) == cx.G1.msm_naive(bases, sc[:7])
+
+
+@pytest.mark.parametrize("curve", ALL_CURVES)
+def test_setup_matches_oracle(curve):
+    """generate_parameters_with_qap (generator.rs:47-208): every query of the GPU-built key equals the oracle's."""
+    c = P.CURVES[curve]
+    cx = P.ctx(c)
+    g = engine(curve)
+    rng = P.Rng(11)
+    cs = P.silly_circuit(c, rng.fr(c.r), rng.fr(c.r))
+    tw = toxic(c, 21)
+    want = pk_to_abi(P.generate_parameters(cs, *tw))
+    got = g.generate_parameters_with_qap(matrices_from_r1cs(cs), *tw, cx.g1_gen(), cx.g2_gen())
+    for f in ("a_query", "b_g1_query", "b_g2_query", "h_query", "l_query", "beta_g1", "delta_g1"):
+        assert np.array_equal(np.asarray(getattr(got, f)).ravel(), np.asarray(getattr(want, f)).ravel()), f
+    for f in ("alpha_g1", "beta_g2", "gamma_g2", "delta_g2", "gamma_abc_g1"):
+        assert np.array_equal(np.asarray(getattr(got.vk, f)).ravel(), np.asarray(getattr(want.vk, f)).ravel()), f
+
+
+@pytest.mark.parametrize("curve", ALL_CURVES)
+def test_prove_silly_circuit(curve):
+    """src/test.rs:45-73 test_prove_and_verify: setup -> prove -> verify true for c = a*b, false for a wrong input;
+    plus bit-exact equality with the oracle's prover on the same (pk, witness, r, s), r = 0 path included."""
+    c = P.CURVES[curve]
+    g = engine(curve)
+    cd = g.codec
+    rng = P.Rng(3)
+    tw = toxic(c, 22)
+    for it in range(3):
+        a, b = rng.fr(c.r), rng.fr(c.r)
+        cs = P.silly_circuit(c, a, b)
+        opk = P.generate_parameters(cs, *tw)
+        m = matrices_from_r1cs(cs)
+        g.load_matrices(m)
+        g.load_proving_key(pk_to_abi(opk))
+        r_, s_ = (0, rng.fr(c.r)) if it == 2 else (rng.fr(c.r), rng.fr(c.r))
+        pf = proof_from_abi(curve, g.create_proof_with_reduction_and_matrices(
+            None, r_, s_, None, cs.num_instance, cs.num_constraints, cd.fr.enc(cs.assignment)))
+        want = P.create_proof(opk, cs, r_, s_)
+        assert (pf.a, pf.b, pf.c) == (want.a, want.b, want.c)
+        if it == 0:
+            assert P.verify_proof(opk.vk, c, pf, [a * b % c.r])
+            assert not P.verify_proof(opk.vk, c, pf, [a])
+
+
+@pytest.mark.parametrize("curve", ["bls12_377", "bls12_381"])
+def test_prove_mimc(curve):
+    """tests/mimc.rs:145-229 (BLS12-377 is the reference's curve for this test; BASELINE config 1 names BLS12-381):
+    key built by the GPU setup, proof checked against the closed form in the exponent and by the pairing verifier."""
+    c = P.CURVES[curve]
+    cx = P.ctx(c)
+    g = engine(curve)
+    cd = g.codec
+    rng = P.Rng(9)
+    constants = [rng.fr(c.r) for _ in range(P.MIMC_ROUNDS)]
+    xl, xr = rng.fr(c.r), rng.fr(c.r)
+    cs = P.mimc_circuit(c, xl, xr, constants)
+    assert cs.is_satisfied() and cs.num_constraints == 644 and cs.assignment[1] == P.mimc_hash(c, xl, xr, constants)
+    tw = toxic(c, 23)
+    m = matrices_from_r1cs(cs)
+    pk_abi = g.generate_parameters_with_qap(m, *tw, cx.g1_gen(), cx.g2_gen())
+    exps = P.generate_parameters(cs, *tw, scalars_only=True)
+    opk = pk_from_abi(curve, pk_abi, toxic=dict(exps, g1=cx.g1_gen(), g2=cx.g2_gen()))
+    r_, s_ = rng.fr(c.r), rng.fr(c.r)
+    z = cd.fr.enc(cs.assignment)
+    # witness map alone (r1cs_to_qap.rs:172-235)
+    h = cd.fr.dec(g.witness_map_from_matrices(None, cs.num_instance, cs.num_constraints, z))
+    assert h == P.witness_map(cs)
+    pf = proof_from_abi(curve, g.create_proof_with_reduction_and_matrices(None, r_, s_, None, cs.num_instance,
+                                                                          cs.num_constraints, z))
+    want = P.proof_in_the_exponent(opk, cs, r_, s_, h=h)
+    assert (pf.a, pf.b, pf.c) == (want.a, want.b, want.c)
+    assert P.verify_proof(opk.vk, c, pf, [cs.assignment[1]])
+    assert not P.verify_proof(opk.vk, c, pf, [xl])
+
+
+def test_sharded_prove_equals_single():
+    """splitting every query by index range over `world` ranks and summing the partial points gives
+    the same proof bit for bit (here: 3 ranks emulated sequentially on one GPU)."""
+    curve = "bn254"
+    c = P.CURVES[curve]
+    cx = P.ctx(c)
+    g = engine(curve)
+    cd = g.codec
+    cs = P.synthetic_circuit(c, 50, seed=4, num_inputs=2)
+    assert cs.is_satisfied()
+    tw = toxic(c, 24)
+    m = matrices_from_r1cs(cs)
+    pk_abi = g.generate_parameters_with_qap(m, *tw, cx.g1_gen(), cx.g2_gen())
+    rng = P.Rng(12)
+    r_, s_ = rng.fr(c.r), rng.fr(c.r)
+    z = np.ascontiguousarray(cd.fr.enc(cs.assignment))
+    single = g.create_proof_with_reduction_and_matrices(None, r_, s_, None, cs.num_instance, cs.num_constraints, z)
+    world = 3
+    parts = []
+    rl = np.ascontiguousarray(cd.fr.enc1(r_))
+    for rank in range(world):
+        g.load_proving_key(pk_abi, rank, world)
+        out = np.zeros(g.partial_limbs(), dtype=np.uint64)
+        g.prove_partial_raw(rl, z.ctypes.data, 0, out)
+        parts.append(out)
+    sharded = g.prove_assemble(r_, s_, np.stack(parts))
+    assert np.array_equal(single.a, sharded.a) and np.array_equal(single.b, sharded.b) and np.array_equal(single.c, sharded.c)
+    exps = P.generate_parameters(cs, *tw, scalars_only=True)
+    opk = pk_from_abi(curve, pk_abi, toxic=dict(exps, g1=cx.g1_gen(), g2=cx.g2_gen()))
+    want = P.proof_in_the_exponent(opk, cs, r_, s_)
+    pf = proof_from_abi(curve, sharded)
+    assert (pf.a, pf.b, pf.c) == (want.a, want.b, want.c)

@@ -5,7 +5,9 @@
 // msm.cuh, the O(1) tail (six scalar multiplications, sums, into_affine) runs on the host with the same field code.
 #pragma once
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <chrono>
+#include <cstdlib>
 #include <cstdio>
 #include <string>
 #include <vector>
@@ -116,10 +118,34 @@ struct Engine : IEngine {
   bool have_pk = false;
   uint32_t rank = 0, world = 1;
   struct Query {
-    DevBuf bases, mask;
+    DevBuf bases, mask;   // bases: geom.copies * (hi - lo) affine points, copy-major (copy j = 2^(c*ne*j) * P)
     uint64_t pairs = 0;   // full MSM length
     uint64_t lo = 0, hi = 0;
+    MsmGeom geom{};
   } q[5];
+  // MSM tuning knobs (environment: G16_MSM_C, G16_MSM_NE, G16_MSM_MAXCOPIES)
+  int cfg_c = 0;          // 0 = pick from n
+  int cfg_ne = 1;         // effective windows with precomputed bases; 0 = no precomputation
+  int cfg_maxcopies = MSM_MAX_COPIES;
+  MsmGeom pick_geom(uint64_t cnt) const {
+    if (cfg_ne <= 0) return msm_geom(cnt, FR_BITS, cfg_c, 0);
+    MsmGeom g = msm_geom(cnt, FR_BITS, cfg_c, cfg_ne);
+    int ne = cfg_ne;
+    while (g.copies > cfg_maxcopies) g = msm_geom(cnt, FR_BITS, cfg_c, ++ne);
+    return g;
+  }
+  template <class F>
+  int finish_query(Query& x) {   // x.bases holds copy 0; build the other copies and the infinity mask
+    const uint64_t cnt = x.hi - x.lo;
+    G16_CUDA(x.mask.reserve(cnt + 16));
+    if (!cnt) return G16_OK;
+    msm_inf_mask<F><<<(unsigned)((cnt + 255) / 256), 256, 0, st_main>>>(x.bases.template as<Affine<F>>(), (uint32_t)cnt, x.mask.template as<uint8_t>());
+    if (x.geom.copies > 1)
+      msm_precompute<F><<<(unsigned)((cnt + 127) / 128), 128, 0, st_main>>>(x.bases.template as<Affine<F>>(), (uint32_t)cnt, x.geom.copies,
+                                                                            x.geom.c * x.geom.ne, x.bases.template as<Affine<F>>());
+    G16_CUDA(cudaGetLastError());
+    return G16_OK;
+  }
   A1 a0, b1_0, alpha_g1, beta_g1, delta_g1;
   A2 b2_0, beta_g2, delta_g2;
   // setup-only extras for pk_export
@@ -135,6 +161,10 @@ struct Engine : IEngine {
     cudaDeviceProp prop;
     G16_CUDA(cudaGetDeviceProperties(&prop, dev));
     if (prop.major < 10) return fail(G16_ERR_CUDA, "device is not sm_100-class (this library ships sm_100a code only)");
+    if (const char* v = getenv("G16_MSM_C")) cfg_c = atoi(v);
+    if (const char* v = getenv("G16_MSM_NE")) cfg_ne = atoi(v);
+    if (const char* v = getenv("G16_MSM_MAXCOPIES")) cfg_maxcopies = std::max(1, std::min(atoi(v), (int)MSM_MAX_COPIES));
+    if (cfg_c < 0 || cfg_c > 24) cfg_c = 0;
     G16_CUDA(cudaStreamCreateWithFlags(&st_main, cudaStreamNonBlocking));
     for (int i = 0; i < 5; i++) G16_CUDA(cudaStreamCreateWithFlags(&st_msm[i], cudaStreamNonBlocking));
     G16_CUDA(cudaEventCreate(&ev_start));
@@ -282,7 +312,7 @@ struct Engine : IEngine {
       G16_CUDA(cudaMemcpyAsync(db.p, bases, n * sizeof(Affine<F>), cudaMemcpyHostToDevice, st_main));
       G16_CUDA(cudaMemcpyAsync(ds.p, scalars, n * 32, cudaMemcpyHostToDevice, st_main));
       msm_inf_mask<F><<<(unsigned)((n + 255) / 256), 256, 0, st_main>>>(db.template as<Affine<F>>(), (uint32_t)n, dm.template as<uint8_t>());
-      const MsmGeom g = msm_geom(n, FR_BITS);
+      const MsmGeom g = msm_geom(n, FR_BITS, cfg_c, 0);   // caller-supplied bases: no precomputed copies
       cudaError_t e = msm_enqueue<F, Fr>(st_main, ws, g, db.template as<Affine<F>>(), dm.template as<uint8_t>(), ds.template as<uint32_t>(), false, &ctr);
       if (e != cudaSuccess) { db.release(); ds.release(); dm.release(); return fail(G16_ERR_CUDA, std::string("msm_enqueue: ") + cudaGetErrorString(e)); }
       e = cudaStreamSynchronize(st_main);
@@ -339,20 +369,18 @@ struct Engine : IEngine {
     x.pairs = pairs;
     x.lo = pairs * rank / world;
     x.hi = pairs * (rank + 1) / world;
+    x.geom = pick_geom(x.hi - x.lo);
   }
   template <class F>
   int upload_query(Query& x, const uint64_t* host_full, uint64_t skip_first) {
     using AT = Affine<F>;
     const uint64_t cnt = x.hi - x.lo;
-    G16_CUDA(x.bases.reserve(cnt * sizeof(AT) + 16));
-    G16_CUDA(x.mask.reserve(cnt + 16));
+    G16_CUDA(x.bases.reserve((size_t)x.geom.copies * cnt * sizeof(AT) + 16));
     if (cnt) {
       const size_t limbs = sizeof(AT) / 8;
-      G16_CUDA(cudaMemcpy(x.bases.p, host_full + (skip_first + x.lo) * limbs, cnt * sizeof(AT), cudaMemcpyHostToDevice));
-      msm_inf_mask<F><<<(unsigned)((cnt + 255) / 256), 256, 0, st_main>>>(x.bases.template as<AT>(), (uint32_t)cnt, x.mask.template as<uint8_t>());
-      G16_CUDA(cudaGetLastError());
+      G16_CUDA(cudaMemcpyAsync(x.bases.p, host_full + (skip_first + x.lo) * limbs, cnt * sizeof(AT), cudaMemcpyHostToDevice, st_main));
     }
-    return G16_OK;
+    return finish_query<F>(x);
   }
   uint64_t nvars() const { return (uint64_t)num_inputs + num_witness; }
   int pk_load(const g16_pk_desc* pk, uint32_t rk, uint32_t wd) override {
@@ -460,7 +488,8 @@ struct Engine : IEngine {
     G16_CUDA(full_a.reserve(nv * sizeof(A1))); G16_CUDA(full_b1.reserve(nv * sizeof(A1))); G16_CUDA(full_b2.reserve(nv * sizeof(A2)));
     G16_CUDA(d_gamma_abc.reserve((size_t)ni * sizeof(A1)));
     shard(q[M_H], n - 1); shard(q[M_L], num_witness); shard(q[M_A], nv - 1); shard(q[M_B1], nv - 1); shard(q[M_B2], nv - 1);
-    G16_CUDA(q[M_H].bases.reserve((n - 1) * sizeof(A1) + 16)); G16_CUDA(q[M_L].bases.reserve((size_t)num_witness * sizeof(A1) + 16));
+    G16_CUDA(q[M_H].bases.reserve((size_t)q[M_H].geom.copies * (n - 1) * sizeof(A1) + 16));
+    G16_CUDA(q[M_L].bases.reserve((size_t)q[M_L].geom.copies * num_witness * sizeof(A1) + 16));
     // a_query / b_g1_query / b_g2_query
     G16_CUDA(up(qa)); if ((rc = batch_mul<Fq>(g1, d_s.template as<Fr>(), nv, full_a.template as<A1>(), tab1))) return rc;
     G16_CUDA(cudaStreamSynchronize(st_main));
@@ -475,7 +504,7 @@ struct Engine : IEngine {
     G16_CUDA(cudaStreamSynchronize(st_main));
     // MSM views: query[1..]
     auto view = [&](Query& x, DevBuf& full, size_t esz) -> int {
-      G16_CUDA(x.bases.reserve((nv - 1) * esz + 16));
+      G16_CUDA(x.bases.reserve((size_t)x.geom.copies * (nv - 1) * esz + 16));
       if (nv > 1) G16_CUDA(cudaMemcpyAsync(x.bases.p, (char*)full.p + esz, (nv - 1) * esz, cudaMemcpyDeviceToDevice, st_main));
       return G16_OK;
     };
@@ -483,13 +512,8 @@ struct Engine : IEngine {
     if ((rc = view(q[M_B1], full_b1, sizeof(A1)))) return rc;
     if ((rc = view(q[M_B2], full_b2, sizeof(A2)))) return rc;
     for (int m = 0; m < 5; m++) {
-      const uint64_t cnt = q[m].hi - q[m].lo;
-      G16_CUDA(q[m].mask.reserve(cnt + 16));
-      if (!cnt) continue;
-      if (m == M_B2) msm_inf_mask<Fq2><<<(unsigned)((cnt + 255) / 256), 256, 0, st_main>>>(q[m].bases.template as<A2>(), (uint32_t)cnt, q[m].mask.template as<uint8_t>());
-      else msm_inf_mask<Fq><<<(unsigned)((cnt + 255) / 256), 256, 0, st_main>>>(q[m].bases.template as<A1>(), (uint32_t)cnt, q[m].mask.template as<uint8_t>());
+      if ((rc = (m == M_B2) ? finish_query<Fq2>(q[m]) : finish_query<Fq>(q[m]))) return rc;
     }
-    G16_CUDA(cudaGetLastError());
     G16_CUDA(cudaMemcpyAsync(&a0, full_a.p, sizeof(A1), cudaMemcpyDeviceToHost, st_main));
     G16_CUDA(cudaMemcpyAsync(&b1_0, full_b1.p, sizeof(A1), cudaMemcpyDeviceToHost, st_main));
     G16_CUDA(cudaMemcpyAsync(&b2_0, full_b2.p, sizeof(A2), cudaMemcpyDeviceToHost, st_main));
@@ -578,7 +602,7 @@ struct Engine : IEngine {
     bool run[5];
     for (int m = 0; m < 5; m++) {
       const uint64_t cnt = q[m].hi - q[m].lo;
-      geom[m] = msm_geom(cnt, FR_BITS);
+      geom[m] = q[m].geom;
       run[m] = cnt > 0 && !(m == M_B1 && r_zero);                        // prover.rs:98: B in G1 skipped when r == 0
       tm.msm_pairs[m] = run[m] ? cnt : 0;
     }
@@ -622,7 +646,7 @@ struct Engine : IEngine {
     tm.total_ms = tot;
     tm.launches = ctr.launches + ntt_launches - l0;
     tm.d2h_bytes = 0;
-    for (int m = 0; m < 5; m++) if (run[m]) tm.d2h_bytes += (uint64_t)geom[m].W * (m == M_B2 ? sizeof(P2) : sizeof(P1));
+    for (int m = 0; m < 5; m++) if (run[m]) tm.d2h_bytes += (uint64_t)geom[m].ne * (m == M_B2 ? sizeof(P2) : sizeof(P1));
     return G16_OK;
   }
   void store_partials(uint64_t* p, const Partials& x) {

@@ -366,6 +366,32 @@ static Jac<F> msm_parallel(const Aff<F>* bases, const u64* scalars, size_t n, in
   return r;
 }
 
+
+// Fixed-base batch multiplication out[i] = scalars[i] * g (BatchMulPreprocessing::batch_mul, generator.rs:129-183):
+// 8-bit windows, table of 32 x 255 Jacobian multiples, one inversion per output.  scalars: Montgomery Fr.
+template <class F, class Fr>
+static void batch_mul(const Aff<F>& g, const Fr* scalars, size_t n, Aff<F>* out, int threads) {
+  std::vector<Jac<F>> table(32 * 255);
+  Jac<F> base = Jac<F>::from_affine(g);
+  for (int w = 0; w < 32; w++) {
+    Jac<F> acc = base;
+    for (int d = 1; d <= 255; d++) { table[w * 255 + d - 1] = acc; acc.add(base); }
+    base = acc;  // 256 * base
+  }
+  const size_t grain = 256, tasks = (n + grain - 1) / grain;
+  parallel_for(tasks, threads, [&](size_t t) {
+    for (size_t i = t * grain; i < std::min(n, (t + 1) * grain); i++) {
+      Fr c = Fr::from_mont(scalars[i]);
+      Jac<F> acc = Jac<F>::inf();
+      for (int w = 0; w < 32; w++) {
+        unsigned d = (unsigned)(c.v[w / 8] >> (8 * (w % 8))) & 0xff;
+        if (d) acc.add(table[w * 255 + d - 1]);
+      }
+      out[i] = acc.to_affine();
+    }
+  });
+}
+
 // ------------------------------------------------------------------------------------------------
 // Radix-2 domain (ark-poly semantics: natural order in/out)
 // ------------------------------------------------------------------------------------------------
@@ -615,11 +641,11 @@ static void init_all() {
   g_init = true;
 }
 
-#define DISPATCH(curve, CALL)        \
+#define DISPATCH(curve, ...)         \
   switch (curve) {                   \
-    case 0: { using C = C381; CALL; } \
-    case 1: { using C = C254; CALL; } \
-    case 2: { using C = C377; CALL; } \
+    case 0: { using C = C381; __VA_ARGS__; } \
+    case 1: { using C = C254; __VA_ARGS__; } \
+    case 2: { using C = C377; __VA_ARGS__; } \
     default: return 2;               \
   }
 
@@ -661,6 +687,26 @@ int orc_msm_g2(int curve, const u64* bases, const u64* scalars, u64 n, u64* out,
     using Fr = decltype(C::make_domain(0, 1).omega);
     auto r = msm_parallel<Fq2>(reinterpret_cast<const A2*>(bases), scalars, n, Fr::BITS, threads);
     C::template store_proj<Fq2>(out, r);
+    return 0;
+  })
+}
+int orc_batch_mul_g1(int curve, const u64* g, const u64* scalars, u64 n, u64* out, int threads) {
+  init_all();
+  DISPATCH(curve, {
+    using A1 = typename C::A1;
+    using Fq = decltype(A1().x);
+    using Fr = decltype(C::make_domain(0, 1).omega);
+    batch_mul<Fq, Fr>(*reinterpret_cast<const A1*>(g), reinterpret_cast<const Fr*>(scalars), n, reinterpret_cast<A1*>(out), threads);
+    return 0;
+  })
+}
+int orc_batch_mul_g2(int curve, const u64* g, const u64* scalars, u64 n, u64* out, int threads) {
+  init_all();
+  DISPATCH(curve, {
+    using A2 = typename C::A2;
+    using Fq2 = decltype(A2().x);
+    using Fr = decltype(C::make_domain(0, 1).omega);
+    batch_mul<Fq2, Fr>(*reinterpret_cast<const A2*>(g), reinterpret_cast<const Fr*>(scalars), n, reinterpret_cast<A2*>(out), threads);
     return 0;
   })
 }

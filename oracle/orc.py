@@ -133,3 +133,22 @@ def prove(cid, nq, pk, m, z, r, s, threads=1):
         raise ValueError("PolynomialDegreeTooLarge")
     assert rc == 0
     return proof, [tms[0], tms[1]]
+
+
+def batch_mul_g1(cid, nq, g, scalars, threads=1):
+    """out[i] = scalars[i] * g (Montgomery Fr scalars) as affine ABI points."""
+    g = np.ascontiguousarray(g, dtype=np.uint64)
+    scalars = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
+    out = np.zeros((scalars.shape[0], 2 * nq), dtype=np.uint64)
+    rc = lib().orc_batch_mul_g1(cid, _p(g), _p(scalars), C.c_uint64(scalars.shape[0]), _p(out), threads)
+    assert rc == 0
+    return out
+
+
+def batch_mul_g2(cid, nq, g, scalars, threads=1):
+    g = np.ascontiguousarray(g, dtype=np.uint64)
+    scalars = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
+    out = np.zeros((scalars.shape[0], 4 * nq), dtype=np.uint64)
+    rc = lib().orc_batch_mul_g2(cid, _p(g), _p(scalars), C.c_uint64(scalars.shape[0]), _p(out), threads)
+    assert rc == 0
+    return out

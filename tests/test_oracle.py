@@ -154,3 +154,17 @@ def test_workload_generators_are_satisfiable(curve):
     cs2 = P.R1CS(c, 2, m2.num_witness_variables, rows(m2.a), rows(m2.b), rows(m2.c), z2i)
     ref = P.dummy_circuit(c, z2i[2], z2i[3], 40, 40)
     assert cs2.is_satisfied() and cs2.a == ref.a and cs2.b == ref.b and cs2.c == ref.c and z2i == ref.assignment
+
+
+@pytest.mark.parametrize("curve", ALL_CURVES)
+def test_oracle_batch_mul(curve):
+    """fixed-base batch multiplication (generator.rs:129-183) vs scalar multiplication in pyref."""
+    c = P.CURVES[curve]
+    cx = P.ctx(c)
+    cd = CurveCodec(get_curve(curve))
+    rng = P.Rng(50)
+    sc = [0, 1, c.r - 1] + [rng.fr(c.r) for _ in range(5)]
+    g1 = cd.enc_g1([cx.g1_gen()])[0]
+    g2 = cd.enc_g2([cx.g2_gen()])[0]
+    assert cd.dec_g1(orc.batch_mul_g1(c.cid, cd.nq, g1, cd.fr.enc(sc), threads=2)) == [cx.G1.mul(cx.g1_gen(), k) for k in sc]
+    assert cd.dec_g2(orc.batch_mul_g2(c.cid, cd.nq, g2, cd.fr.enc(sc), threads=2)) == [cx.G2.mul(cx.g2_gen(), k) for k in sc]

@@ -98,6 +98,21 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
+def host_threads(requested=0):
+    """Threads for the CPU arm: min(affinity, cgroup CPU quota) -- the GPU boxes expose 128 logical CPUs under a 16-CPU quota,
+    and oversubscribing a quota only adds contention."""
+    if requested > 0:
+        return requested
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(int(q) / int(p) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
 def measured_peak_hbm():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -188,7 +203,7 @@ def run_reference(a):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import orc
     from groth16_b200 import CurveCodec, get_curve
-    threads = a.cpu_threads or orc.hw_threads()
+    threads = host_threads(a.cpu_threads)
     cp = get_curve(a.curve)
     cd = CurveCodec(cp)
     m, z, pub, _ = build_workload(a)
@@ -253,8 +268,10 @@ def run_cuda(a):
     G = GENERATORS[g.curve.name]
     t = time.time()
     pk = g.generate_parameters_with_qap(m, *TOXIC, G["g1"], G["g2"], export=(world > 1 or not a.no_cpu_baseline))
+    sp = None
     if world > 1:
-        g.load_proving_key(pk, rank, world)   # keep this rank's index range of every query
+        from groth16_b200.dist import ShardedProver
+        sp = ShardedProver(g, pk, None, rank, world, dev)   # keep this rank's index range of every query
     t_setup = time.time() - t
     r = np.ascontiguousarray(cd.fr.enc1(123456789))
     s = np.ascontiguousarray(cd.fr.enc1(987654321))
@@ -262,22 +279,12 @@ def run_cuda(a):
     z_pinned = torch.from_numpy(z_np.view(np.int64)).pin_memory()
     z_dev = z_pinned.to(dev)
     proof = np.zeros(8 * nq, dtype=np.uint64)
-    pl = g.partial_limbs()
-    part_host = torch.zeros(pl, dtype=torch.int64).pin_memory()
-    part_np = part_host.numpy().view(np.uint64)
-    gathered = torch.zeros(world * pl, dtype=torch.int64, device=dev) if world > 1 else None
-    gathered_host = torch.zeros(world * pl, dtype=torch.int64).pin_memory() if world > 1 else None
-
     def step(zptr, flags):
         """one proof; returns the proof limbs (every rank computes the same proof)"""
         if world == 1:
             g.prove_raw(r, s, zptr, flags, proof)
             return proof
-        g.prove_partial_raw(r, zptr, flags, part_np)
-        mine = part_host.to(dev, non_blocking=True)
-        dist.all_gather_into_tensor(gathered, mine)                       # 5 points per rank over NCCL / NVLink
-        gathered_host.copy_(gathered, non_blocking=False)
-        pf = g.prove_assemble(r, s, gathered_host.numpy().view(np.uint64))
+        pf = sp.prove(r, s, zptr, flags)   # partial MSMs -> NCCL all_gather of 5 points per rank -> assemble
         proof[:2 * nq] = pf.a; proof[2 * nq:6 * nq] = pf.b; proof[6 * nq:] = pf.c
         return proof
 
@@ -361,7 +368,7 @@ def run_cuda(a):
         if world == 1 and not a.no_cpu_baseline:
             sys.path.insert(0, os.path.join(ROOT, "oracle"))
             import orc
-            threads = a.cpu_threads or orc.hw_threads()
+            threads = host_threads(a.cpu_threads)
             cproof, csec, tms = cpu_prove_once(a, cd, nq, pk, m, z_np, r, s, threads)
             if not np.array_equal(cproof, first):
                 raise SystemExit("PARITY FAILURE: CUDA proof != CPU oracle proof at full size")

@@ -1,0 +1,48 @@
+"""Multi-GPU plumbing (one process per GPU, torch.distributed): SURVEY.md section 8e.
+
+Every MSM's (scalar, base) pairs are split by contiguous index range over the ranks; each rank's context keeps only its
+range of every query resident (g16_pk_load(rank, world)).  Per proof a rank computes five partial sums
+(g16_prove_partial), the 5 affine points per rank are all-gathered (NCCL on GPUs, gloo in the CPU tests) and every rank
+assembles the same proof (g16_prove_assemble).  EC addition is exactly associative and commutative, so the proof is
+bit-identical for any world size; NCCL has no user-defined reduction for curve points, hence gather-then-add.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_range(pairs: int, rank: int, world: int):
+    """Index range of an MSM of `pairs` pairs owned by `rank` -- must match Engine::shard in csrc/engine.cuh."""
+    return pairs * rank // world, pairs * (rank + 1) // world
+
+
+def all_gather_partials(partial: np.ndarray, device=None) -> np.ndarray:
+    """partial: uint64 limbs of this rank's five partial points -> (world, limbs) array, rank order."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    t = torch.from_numpy(np.ascontiguousarray(partial, dtype=np.uint64).view(np.int64))
+    if device is not None:
+        t = t.to(device)
+    out = torch.empty(world * t.numel(), dtype=torch.int64, device=t.device)
+    dist.all_gather_into_tensor(out, t)
+    return out.cpu().numpy().view(np.uint64).reshape(world, -1)
+
+
+class ShardedProver:
+    """Groth16 prover over `world` GPUs for one resident circuit + key."""
+
+    def __init__(self, groth16, pk, matrices, rank: int, world: int, device=None):
+        self.g = groth16
+        self.rank, self.world, self.device = rank, world, device
+        if matrices is not None:
+            self.g.load_matrices(matrices)
+        self.g.load_proving_key(pk, rank, world)
+        self._partial = np.zeros(self.g.partial_limbs(), dtype=np.uint64)
+
+    def prove(self, r, s, z_ptr: int, flags: int = 0):
+        """r, s: Montgomery limbs; z_ptr: address of the full assignment (host or device per `flags`)."""
+        rl = self.g._fr_arg(r)
+        self.g.prove_partial_raw(rl, z_ptr, flags, self._partial)
+        allp = all_gather_partials(self._partial, self.device) if self.world > 1 else self._partial[None, :]
+        return self.g.prove_assemble(rl, self.g._fr_arg(s), allp)

@@ -139,22 +139,36 @@ struct Fp {
   }
   static Fp neg(const Fp& a) { return a.is_zero() ? a : sub(zero(), a); }
   static Fp dbl(const Fp& a) { return add(a, a); }
-  static Fp mul(const Fp& a, const Fp& b) {  // CIOS
-    u64 t[N + 2];
-    for (int i = 0; i < N + 2; i++) t[i] = 0;
+  static inline __attribute__((always_inline)) Fp mul(const Fp& a, const Fp& b) {  // CIOS, no-carry variant (spare top bit)
+    u64 P[N];
+#pragma GCC unroll 8
+    for (int i = 0; i < N; i++) P[i] = MOD[i];
+    const u64 inv = INV;
+    u64 t[N];
+#pragma GCC unroll 8
+    for (int i = 0; i < N; i++) t[i] = 0;
+#pragma GCC unroll 8
     for (int i = 0; i < N; i++) {
-      u128 c = 0;
-      for (int j = 0; j < N; j++) { c += (u128)a.v[j] * b.v[i] + t[j]; t[j] = (u64)c; c >>= 64; }
-      c += t[N]; t[N] = (u64)c; t[N + 1] = (u64)(c >> 64);
-      u64 m = t[0] * INV;
-      c = (u128)m * MOD[0] + t[0];
-      c >>= 64;
-      for (int j = 1; j < N; j++) { c += (u128)m * MOD[j] + t[j]; t[j - 1] = (u64)c; c >>= 64; }
-      c += t[N]; t[N - 1] = (u64)c; t[N] = t[N + 1] + (u64)(c >> 64);
+      // t += a * b[i]
+      u128 c = (u128)a.v[0] * b.v[i] + t[0];
+      u64 lo0 = (u64)c;
+      const u64 m = lo0 * inv;
+      u128 d = (u128)m * P[0] + lo0;   // low limb becomes zero
+      u64 c1 = (u64)(c >> 64), c2 = (u64)(d >> 64);
+#pragma GCC unroll 8
+      for (int j = 1; j < N; j++) {
+        c = (u128)a.v[j] * b.v[i] + t[j] + c1;
+        c1 = (u64)(c >> 64);
+        d = (u128)m * P[j] + (u64)c + c2;
+        c2 = (u64)(d >> 64);
+        t[j - 1] = (u64)d;
+      }
+      t[N - 1] = c1 + c2;   // cannot overflow: modulus has a spare top bit (ark-ff's "no-carry" optimisation)
     }
     Fp r;
-    memcpy(r.v, t, sizeof(r.v));
-    if (t[N] || geq_mod(r.v)) sub_mod_inplace(r.v);
+#pragma GCC unroll 8
+    for (int i = 0; i < N; i++) r.v[i] = t[i];
+    if (geq_mod(r.v)) sub_mod_inplace(r.v);
     return r;
   }
   static Fp sqr(const Fp& a) { return mul(a, a); }

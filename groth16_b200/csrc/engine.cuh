@@ -53,36 +53,6 @@ struct IEngine {
 };
 
 // ------------------------------------------------------------------------------------------------
-// fixed-base batch multiplication (BatchMulPreprocessing::batch_mul, generator.rs:129-183)
-// ------------------------------------------------------------------------------------------------
-static constexpr int FB_WINDOWS = 32;  // 8-bit windows over a 256-bit scalar
-template <class F>
-__global__ void fb_table_kernel(Affine<F> g, XYZZ<F>* table /* [32][255] */) {
-  const int w = threadIdx.x;
-  if (w >= FB_WINDOWS) return;
-  XYZZ<F> base = XYZZ<F>::from_affine(g);
-  for (int i = 0; i < 8 * w; i++) base.dbl_inplace();
-  XYZZ<F> acc = base;
-  for (int d = 1; d <= 255; d++) {
-    table[w * 255 + d - 1] = acc;
-    acc.add(base);
-  }
-}
-template <class F, class FrF>
-__global__ void __launch_bounds__(128) fb_mul_kernel(const XYZZ<F>* __restrict__ table, const FrF* __restrict__ scalars,
-                                                     uint32_t n, Affine<F>* __restrict__ out) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const FrF s = FrF::from_mont(ntt_ldg(scalars + i));
-  XYZZ<F> acc = XYZZ<F>::inf();
-  for (int w = 0; w < FB_WINDOWS; w++) {
-    const uint32_t d = (s.v[w >> 2] >> (8 * (w & 3))) & 0xff;
-    if (d) acc.add(table[w * 255 + d - 1]);
-  }
-  out[i] = acc.to_affine();
-}
-
-// ------------------------------------------------------------------------------------------------
 template <class CP>
 struct Engine : IEngine {
   using Fr = Fp<typename CP::FrP>;
@@ -138,12 +108,8 @@ struct Engine : IEngine {
   int finish_query(Query& x) {   // x.bases holds copy 0; build the other copies and the infinity mask
     const uint64_t cnt = x.hi - x.lo;
     G16_CUDA(x.mask.reserve(cnt + 16));
-    if (!cnt) return G16_OK;
-    msm_inf_mask<F><<<(unsigned)((cnt + 255) / 256), 256, 0, st_main>>>(x.bases.template as<Affine<F>>(), (uint32_t)cnt, x.mask.template as<uint8_t>());
-    if (x.geom.copies > 1)
-      msm_precompute<F><<<(unsigned)((cnt + 127) / 128), 128, 0, st_main>>>(x.bases.template as<Affine<F>>(), (uint32_t)cnt, x.geom.copies,
-                                                                            x.geom.c * x.geom.ne, x.bases.template as<Affine<F>>());
-    G16_CUDA(cudaGetLastError());
+    G16_CUDA(msm_prepare_query<F>(st_main, x.bases.template as<Affine<F>>(), (uint32_t)cnt, x.geom.copies, x.geom.c * x.geom.ne,
+                                  x.mask.template as<uint8_t>()));
     return G16_OK;
   }
   A1 a0, b1_0, alpha_g1, beta_g1, delta_g1;
@@ -165,8 +131,17 @@ struct Engine : IEngine {
     if (const char* v = getenv("G16_MSM_NE")) cfg_ne = atoi(v);
     if (const char* v = getenv("G16_MSM_MAXCOPIES")) cfg_maxcopies = std::max(1, std::min(atoi(v), (int)MSM_MAX_COPIES));
     if (cfg_c < 0 || cfg_c > 24) cfg_c = 0;
-    G16_CUDA(cudaStreamCreateWithFlags(&st_main, cudaStreamNonBlocking));
-    for (int i = 0; i < 5; i++) G16_CUDA(cudaStreamCreateWithFlags(&st_msm[i], cudaStreamNonBlocking));
+    // Stream priorities (greatest first): the witness map (H's MSM waits for it), then the G2 MSM (longest latency-bound
+    // tail: its point additions cost ~3x a G1 addition), then H (starts last), then L / A / B-in-G1.  The heavy
+    // accumulation kernels of the low-priority streams fill the machine while the high-priority tails trickle through.
+    int prio_lo = 0, prio_hi = 0;
+    G16_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));   // lo = least priority (numerically greatest)
+    auto level = [&](int k) { return std::min(prio_lo, prio_hi + k); };
+    G16_CUDA(cudaStreamCreateWithPriority(&st_main, cudaStreamNonBlocking, level(0)));
+    for (int i = 0; i < 5; i++) {
+      const int pr = i == M_B2 ? level(1) : (i == M_H ? level(2) : prio_lo);
+      G16_CUDA(cudaStreamCreateWithPriority(&st_msm[i], cudaStreamNonBlocking, pr));
+    }
     G16_CUDA(cudaEventCreate(&ev_start));
     G16_CUDA(cudaEventCreate(&ev_z));
     G16_CUDA(cudaEventCreate(&ev_h));
@@ -311,7 +286,7 @@ struct Engine : IEngine {
       G16_CUDA(dm.reserve(n));
       G16_CUDA(cudaMemcpyAsync(db.p, bases, n * sizeof(Affine<F>), cudaMemcpyHostToDevice, st_main));
       G16_CUDA(cudaMemcpyAsync(ds.p, scalars, n * 32, cudaMemcpyHostToDevice, st_main));
-      msm_inf_mask<F><<<(unsigned)((n + 255) / 256), 256, 0, st_main>>>(db.template as<Affine<F>>(), (uint32_t)n, dm.template as<uint8_t>());
+      G16_CUDA(msm_prepare_query<F>(st_main, db.template as<Affine<F>>(), (uint32_t)n, 1, 0, dm.template as<uint8_t>()));
       const MsmGeom g = msm_geom(n, FR_BITS, cfg_c, 0);   // caller-supplied bases: no precomputed copies
       cudaError_t e = msm_enqueue<F, Fr>(st_main, ws, g, db.template as<Affine<F>>(), dm.template as<uint8_t>(), ds.template as<uint32_t>(), false, &ctr);
       if (e != cudaSuccess) { db.release(); ds.release(); dm.release(); return fail(G16_ERR_CUDA, std::string("msm_enqueue: ") + cudaGetErrorString(e)); }
@@ -419,9 +394,7 @@ struct Engine : IEngine {
   template <class F>
   int batch_mul(const Affine<F>& gen, const Fr* d_scalars, uint64_t cnt, Affine<F>* d_out, DevBuf& table) {
     G16_CUDA(table.reserve((size_t)FB_WINDOWS * 255 * sizeof(XYZZ<F>)));
-    fb_table_kernel<F><<<1, 32, 0, st_main>>>(gen, table.template as<XYZZ<F>>());
-    if (cnt) fb_mul_kernel<F, Fr><<<(unsigned)((cnt + 127) / 128), 128, 0, st_main>>>(table.template as<XYZZ<F>>(), d_scalars, (uint32_t)cnt, d_out);
-    G16_CUDA(cudaGetLastError());
+    G16_CUDA((fb_batch_mul<F, Fr>(st_main, gen, d_scalars, cnt, d_out, table.template as<XYZZ<F>>())));
     return G16_OK;
   }
   int setup(const uint64_t* alpha_, const uint64_t* beta_, const uint64_t* gamma_, const uint64_t* delta_,
@@ -565,8 +538,8 @@ struct Engine : IEngine {
     const uint32_t n = 1u << L;
     CsrDev cs[3];
     for (int m = 0; m < 3; m++) cs[m] = CsrDev{csr_rp[m].template as<uint32_t>(), csr_col[m].template as<uint32_t>(), csr_val[m].p};
-    r1cs_matvec_kernel<Fr><<<(n + 255) / 256, 256, 0, st_main>>>(cs[0], cs[1], cs[2], d_z.template as<Fr>(), num_constraints, num_inputs, n,
-                                                                 d_a.template as<Fr>(), d_b.template as<Fr>(), d_c.template as<Fr>());
+    r1cs_matvec<Fr>(st_main, cs, d_z.template as<Fr>(), num_constraints, num_inputs, n, d_a.template as<Fr>(), d_b.template as<Fr>(),
+                    d_c.template as<Fr>());
     ntt_launches++;
     witness_map_device();
     G16_CUDA(cudaGetLastError());
@@ -729,6 +702,13 @@ struct Engine : IEngine {
     return assemble(load_fr(r), load_fr(s), x, proof);
   }
 };
+
+// extern-template declarations for one curve: put before make_engine<CP> is instantiated (engine_<curve>.cu)
+#define G16_CURVE_KERNELS(X, CP)                                                                  \
+  G16_NTT_TEMPLATES(X, Fp<CP::FrP>)                                                               \
+  G16_MSM_TEMPLATES(X, Fp<CP::FqP>, Fp<CP::FrP>)                                                  \
+  G16_MSM_TEMPLATES(X, G16_FQ2(CP), Fp<CP::FrP>)
+#define G16_FQ2(CP) Fp2<CP::FqP, CP::FQ2_NONRESIDUE_NEG>
 
 template <class CP>
 IEngine* make_engine(int device, int* rc) {

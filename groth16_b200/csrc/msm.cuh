@@ -569,4 +569,67 @@ XYZZ<F> msm_finish(const MsmWorkspace<F>& ws, const MsmGeom& g) {
   return acc;
 }
 
+
+// Make a query resident: identity mask of copy 0 and (copies > 1) the precomputed multiples 2^(shift*j) * P.
+template <class F>
+cudaError_t msm_prepare_query(cudaStream_t st, Affine<F>* d_bases, uint32_t cnt, int copies, int shift, uint8_t* d_mask) {
+  if (!cnt) return cudaSuccess;
+  msm_inf_mask<F><<<(cnt + 255) / 256, 256, 0, st>>>(d_bases, cnt, d_mask);
+  if (copies > 1) msm_precompute<F><<<(cnt + 127) / 128, 128, 0, st>>>(d_bases, cnt, copies, shift, d_bases);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// fixed-base batch multiplication (BatchMulPreprocessing::batch_mul, generator.rs:129-183)
+// ------------------------------------------------------------------------------------------------
+static constexpr int FB_WINDOWS = 32;  // 8-bit windows over a 256-bit scalar
+template <class F>
+__global__ void fb_table_kernel(Affine<F> g, XYZZ<F>* table /* [32][255] */) {
+  const int w = threadIdx.x;
+  if (w >= FB_WINDOWS) return;
+  XYZZ<F> base = XYZZ<F>::from_affine(g);
+  for (int i = 0; i < 8 * w; i++) base.dbl_inplace();
+  XYZZ<F> acc = base;
+  for (int d = 1; d <= 255; d++) {
+    table[w * 255 + d - 1] = acc;
+    acc.add(base);
+  }
+}
+template <class F, class FrF>
+__global__ void __launch_bounds__(128) fb_mul_kernel(const XYZZ<F>* __restrict__ table, const FrF* __restrict__ scalars,
+                                                     uint32_t n, Affine<F>* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  FrF s;
+  {
+    const uint4* p = reinterpret_cast<const uint4*>(scalars + i);
+    uint4 lo = __ldg(p), hi = __ldg(p + 1);
+    s.v[0] = lo.x; s.v[1] = lo.y; s.v[2] = lo.z; s.v[3] = lo.w;
+    s.v[4] = hi.x; s.v[5] = hi.y; s.v[6] = hi.z; s.v[7] = hi.w;
+  }
+  s = FrF::from_mont(s);
+  XYZZ<F> acc = XYZZ<F>::inf();
+  for (int w = 0; w < FB_WINDOWS; w++) {
+    const uint32_t d = (s.v[w >> 2] >> (8 * (w & 3))) & 0xff;
+    if (d) acc.add(table[w * 255 + d - 1]);
+  }
+  out[i] = acc.to_affine();
+}
+// d_table: FB_WINDOWS * 255 XYZZ points of scratch
+template <class F, class FrF>
+cudaError_t fb_batch_mul(cudaStream_t st, const Affine<F>& gen, const FrF* d_scalars, uint64_t cnt, Affine<F>* d_out,
+                         XYZZ<F>* d_table) {
+  fb_table_kernel<F><<<1, 32, 0, st>>>(gen, d_table);
+  if (cnt) fb_mul_kernel<F, FrF><<<(unsigned)((cnt + 127) / 128), 128, 0, st>>>(d_table, d_scalars, (uint32_t)cnt, d_out);
+  return cudaGetLastError();
+}
+
+// Explicit-instantiation lists: kernels are compiled in their own translation units (k_msm_*.cu), the engine TU only
+// declares them `extern template` (keeps ptxas work parallel across make jobs).
+#define G16_MSM_TEMPLATES(X, F, FrF)                                                                                     \
+  X cudaError_t msm_enqueue<F, FrF>(cudaStream_t, MsmWorkspace<F>&, const MsmGeom&, const Affine<F>*, const uint8_t*,    \
+                                    const uint32_t*, bool, MsmCounters*, cudaEvent_t, cudaEvent_t);                      \
+  X cudaError_t msm_prepare_query<F>(cudaStream_t, Affine<F>*, uint32_t, int, int, uint8_t*);                            \
+  X cudaError_t fb_batch_mul<F, FrF>(cudaStream_t, const Affine<F>&, const FrF*, uint64_t, Affine<F>*, XYZZ<F>*);
+
 }  // namespace g16

@@ -318,4 +318,17 @@ void ntt_run(cudaStream_t st, const NttDomain<Fr>& d, bool inverse, const Fr* sr
   }
 }
 
+
+template <class Fr>
+void r1cs_matvec(cudaStream_t st, const CsrDev* cs, const Fr* z, uint32_t nc, uint32_t num_inputs, uint32_t n, Fr* a, Fr* b,
+                 Fr* c) {
+  r1cs_matvec_kernel<Fr><<<(n + 255) / 256, 256, 0, st>>>(cs[0], cs[1], cs[2], z, nc, num_inputs, n, a, b, c);
+}
+
+#define G16_NTT_TEMPLATES(X, Fr)                                                                                       \
+  X void ntt_run<Fr>(cudaStream_t, const NttDomain<Fr>&, bool, const Fr*, Fr*, Fr*, int, const Fr*, const Fr*, const Fr*, \
+                     const Fr&, int, const Fr*, const Fr&, unsigned long long*);                                       \
+  X cudaError_t ntt_domain_build<Fr>(NttDomain<Fr>&, int, cudaStream_t, unsigned long long*);                          \
+  X void r1cs_matvec<Fr>(cudaStream_t, const CsrDev*, const Fr*, uint32_t, uint32_t, uint32_t, Fr*, Fr*, Fr*);
+
 }  // namespace g16

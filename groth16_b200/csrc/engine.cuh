@@ -288,7 +288,7 @@ struct Engine : IEngine {
       G16_CUDA(cudaMemcpyAsync(ds.p, scalars, n * 32, cudaMemcpyHostToDevice, st_main));
       G16_CUDA(msm_prepare_query<F>(st_main, db.template as<Affine<F>>(), (uint32_t)n, 1, 0, dm.template as<uint8_t>()));
       const MsmGeom g = msm_geom(n, FR_BITS, cfg_c, 0);   // caller-supplied bases: no precomputed copies
-      cudaError_t e = msm_enqueue<F, Fr>(st_main, ws, g, db.template as<Affine<F>>(), dm.template as<uint8_t>(), ds.template as<uint32_t>(), false, &ctr);
+      cudaError_t e = msm_enqueue<F, Fr>(st_main, ws, g, db.template as<Affine<F>>(), dm.template as<uint8_t>(), ds.template as<uint32_t>(), false, &ctr, nullptr, nullptr);
       if (e != cudaSuccess) { db.release(); ds.release(); dm.release(); return fail(G16_ERR_CUDA, std::string("msm_enqueue: ") + cudaGetErrorString(e)); }
       e = cudaStreamSynchronize(st_main);
       db.release(); ds.release(); dm.release();
@@ -619,7 +619,8 @@ struct Engine : IEngine {
     tm.total_ms = tot;
     tm.launches = ctr.launches + ntt_launches - l0;
     tm.d2h_bytes = 0;
-    for (int m = 0; m < 5; m++) if (run[m]) tm.d2h_bytes += (uint64_t)geom[m].ne * (m == M_B2 ? sizeof(P2) : sizeof(P1));
+    for (int m = 0; m < 5; m++)
+      if (run[m]) tm.d2h_bytes += (m == M_B2 ? ws2.plan.leaf_pts * sizeof(P2) : ws1[m].plan.leaf_pts * sizeof(P1)) * geom[m].ne;
     return G16_OK;
   }
   void store_partials(uint64_t* p, const Partials& x) {

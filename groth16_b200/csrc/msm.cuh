@@ -12,9 +12,8 @@
 //                          mixed-adds them (XYZZ += affine, gathered from the resident base array), writes buckets
 //                          that are complete inside its chunk and emits <= 2 boundary partials
 //   5. msm_accum_ln        the same reduction over the partial list, level by level, until one thread remains
-//   6. msm_bucket_reduce   per (window, segment of L buckets): running-sum trick + (segment offset) * sum
-//   7. msm_sum_groups      tree-sum of the segment results -> one point per window
-//   host: Horner over windows (c doublings each), prover.rs semantics preserved.
+//   6. msm_sum_strided     bucket reduction sum_b (b+1) B_b as two rounds of row / column block-tree sums
+//   host: weighted sums of the <= 64-point leaf arrays, Horner over effective windows; prover.rs semantics preserved.
 // Skewed scalar distributions (boolean witnesses, the reference's DummyCircuit whose witness is constant,
 // benches/bench.rs:43-54) cost the same as uniform ones: work is split by sorted position, not by bucket.
 #pragma once
@@ -209,9 +208,11 @@ struct MsmEmit {
       if (head) wrote_head = true; else wrote_tail = true;
     }
   }
-  __device__ __forceinline__ void finish() {
+  // returns the number of partials this thread emitted
+  __device__ __forceinline__ uint32_t finish() {
     if (!wrote_head) okeys[2 * t] = MSM_INVALID;
     if (!wrote_tail) okeys[2 * t + 1] = MSM_INVALID;
+    return (wrote_head ? 1u : 0u) + (wrote_tail ? 1u : 0u);
   }
 };
 
@@ -233,9 +234,10 @@ __global__ void __launch_bounds__(128) msm_accum_l0(const Affine<F>* __restrict_
                                                     const uint32_t* __restrict__ skey,
                                                     const uint32_t* __restrict__ total_ptr, uint64_t T0,
                                                     XYZZ<F>* __restrict__ buckets, uint32_t* __restrict__ okeys,
-                                                    XYZZ<F>* __restrict__ opts) {
+                                                    XYZZ<F>* __restrict__ opts, uint32_t* pending0) {
   const uint32_t M = *total_ptr;
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t == 0) *pending0 = 1;   // level 0 always hands a (possibly empty) partial list to level 1
   if (t >= T0) return;
   MsmEmit<F> em{buckets, okeys, opts, t, false, false};
   const uint64_t begin = t * K0;
@@ -262,18 +264,20 @@ __global__ void __launch_bounds__(128) msm_accum_l0(const Affine<F>* __restrict_
   em.finish();
 }
 
-// One level >= 1 for thread t over slots [t*KF, t*KF + KF) of a partial list of S slots.  Keys may contain
-// MSM_INVALID holes; inside a run of equal keys there is at most one hole between neighbours, so a
-// look-back / look-ahead of two slots decides whether a run continues across the chunk boundary.
+// One level >= 1 for thread t over slots [1 + t*KF, 1 + (t+1)*KF) of a partial list of S slots (slot 0, the head of
+// thread 0, is never valid).  The one-slot shift makes chunk boundaries fall between a thread's (head, tail) pair instead
+// of between tail_t and head_{t+1}: with evenly filled buckets every run (tail_t, head_{t+1}) is then interior to a chunk
+// and the whole list resolves in ONE level.  Keys may contain MSM_INVALID holes; inside a run of equal keys there is at
+// most one hole between neighbours, so a look-back / look-ahead of two slots decides whether a run continues
+// across the chunk boundary.  Returns the number of partials emitted.
 template <class F, int KF>
-__device__ __forceinline__ void msm_level_step(const uint32_t* ikeys, const XYZZ<F>* ipts, uint64_t S, uint64_t t,
-                                               XYZZ<F>* buckets, uint32_t* okeys, XYZZ<F>* opts) {
+__device__ __forceinline__ uint32_t msm_level_step(const uint32_t* ikeys, const XYZZ<F>* ipts, uint64_t S, uint64_t t,
+                                                   XYZZ<F>* buckets, uint32_t* okeys, XYZZ<F>* opts) {
   MsmEmit<F> em{buckets, okeys, opts, t, false, false};
-  const uint64_t begin = t * KF;
-  if (begin >= S) { em.finish(); return; }
+  const uint64_t begin = 1 + t * KF;
+  if (begin >= S) return em.finish();
   const uint64_t end = min(S, begin + KF);
-  uint32_t prev = MSM_INVALID, next = MSM_INVALID;
-  if (begin >= 1) prev = ikeys[begin - 1];
+  uint32_t prev = ikeys[begin - 1], next = MSM_INVALID;
   if (prev == MSM_INVALID && begin >= 2) prev = ikeys[begin - 2];
   if (end < S) next = ikeys[end];
   if (next == MSM_INVALID && end + 1 < S) next = ikeys[end + 1];
@@ -297,28 +301,37 @@ __device__ __forceinline__ void msm_level_step(const uint32_t* ikeys, const XYZZ
     }
   }
   if (have) em.flush(cur, acc, first_seg && prev == cur, next == cur);
-  em.finish();
+  return em.finish();
 }
+__host__ __device__ inline uint64_t msm_level_threads(uint64_t S, int KF) { return S <= 1 ? 1 : (S - 1 + KF - 1) / KF; }
+
+// pending[0] = partials emitted by the previous level (level 0 stores a non-zero dummy), pending[1] = ours.
+// A level whose input is empty returns at once; so do all later levels (their input counter stays 0).
 template <class F, int KF>
 __global__ void __launch_bounds__(128) msm_accum_ln(const uint32_t* __restrict__ ikeys,
                                                     const XYZZ<F>* __restrict__ ipts, uint64_t S, uint64_t T,
                                                     XYZZ<F>* __restrict__ buckets, uint32_t* __restrict__ okeys,
-                                                    XYZZ<F>* __restrict__ opts) {
+                                                    XYZZ<F>* __restrict__ opts, uint32_t* pending) {
+  if (pending[0] == 0) return;
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= T) return;
-  msm_level_step<F, KF>(ikeys, ipts, S, t, buckets, okeys, opts);
+  uint32_t emitted = 0;
+  if (t < T) emitted = msm_level_step<F, KF>(ikeys, ipts, S, t, buckets, okeys, opts);
+  const uint32_t any = __syncthreads_count(emitted != 0);
+  if (threadIdx.x == 0 && any) atomicAdd(&pending[1], any);
 }
-// All remaining levels in one block once the partial list is short (S <= 2 * blockDim * KF): no launch gaps.
+// All remaining levels in one block once the partial list is short: no launch gaps.
 template <class F, int KF>
 __global__ void __launch_bounds__(256) msm_accum_tail(uint32_t* k0, XYZZ<F>* p0, uint32_t* k1, XYZZ<F>* p1, uint64_t S,
-                                                      XYZZ<F>* buckets) {
+                                                      XYZZ<F>* buckets, const uint32_t* pending) {
+  if (pending[0] == 0) return;
   uint32_t *ik = k0, *ok = k1;
   XYZZ<F>*ip = p0, *op = p1;
   while (true) {
-    const uint64_t T = (S + KF - 1) / KF;
-    for (uint64_t t = threadIdx.x; t < T; t += blockDim.x) msm_level_step<F, KF>(ik, ip, S, t, buckets, ok, op);
-    __syncthreads();
-    if (T == 1) break;
+    const uint64_t T = msm_level_threads(S, KF);
+    uint32_t emitted = 0;
+    for (uint64_t t = threadIdx.x; t < T; t += blockDim.x) emitted += msm_level_step<F, KF>(ik, ip, S, t, buckets, ok, op);
+    const uint32_t any = __syncthreads_count(emitted != 0);
+    if (T == 1 || any == 0) break;
     S = 2 * T;
     uint32_t* tk = ik; ik = ok; ok = tk;
     XYZZ<F>* tp = ip; ip = op; op = tp;
@@ -326,39 +339,79 @@ __global__ void __launch_bounds__(256) msm_accum_tail(uint32_t* k0, XYZZ<F>* p0,
 }
 
 // ------------------------------------------------------------------------------------------------
-// 6/7. bucket reduction
+// 6/7. bucket reduction:  sum_b (b + 1) * bucket[b]  per effective window
 // ------------------------------------------------------------------------------------------------
-// out[w*nseg + seg] = sum_{j<L} (seg*L + j + 1) * bucket[w*B + seg*L + j]
-template <class F>
-__global__ void __launch_bounds__(128) msm_bucket_reduce(const XYZZ<F>* __restrict__ buckets, uint32_t B, uint32_t L,
-                                                         uint32_t total_segs, XYZZ<F>* __restrict__ out) {
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= total_segs) return;
-  const uint32_t nseg = B / L;
-  const uint32_t w = t / nseg, seg = t % nseg;
-  const XYZZ<F>* base = buckets + (size_t)w * B + (size_t)seg * L;
-  XYZZ<F> running = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
-  for (int j = (int)L - 1; j >= 0; j--) {
-    running.add(base[j]);
-    acc.add(running);
+// Written as plain sums only, so that every step is a shallow tree instead of a long dependent chain of point
+// additions (a single warp needs ~15 us per XYZZ addition):  with b = hi * 2^a0 + lo,
+//     sum_b (b+1) B_b = 2^a0 * sum_hi hi * R_hi + sum_lo (lo+1) * C_lo,   R_hi = sum_lo B[hi,lo],  C_lo = sum_hi B[hi,lo]
+// and the two weighted sums over the short arrays R and C are split the same way once more; what is left (arrays of
+// <= 64 points) is finished on the host, where a point addition costs ~0.6 us.  Each bucket enters two additions, like
+// in the classic running-sum trick.
+//
+// out[o] = sum_{j < len} in[w * win_stride + r * base_mul + j * stride],  o = w * per_win_out + r.
+// `tpo` threads cooperate on one output: strided serial part, then a shared-memory tree.
+template <class F, int TPB>
+__global__ void __launch_bounds__(TPB) msm_sum_strided(const XYZZ<F>* __restrict__ in, XYZZ<F>* __restrict__ out,
+                                                       uint32_t n_out, uint32_t per_win_out, uint32_t win_stride,
+                                                       uint32_t len, uint32_t stride, uint32_t base_mul, uint32_t tpo) {
+  __shared__ XYZZ<F> sm[TPB];
+  const uint32_t g = threadIdx.x / tpo, l = threadIdx.x % tpo;
+  const uint32_t o = blockIdx.x * (TPB / tpo) + g;
+  XYZZ<F> acc = XYZZ<F>::inf();
+  if (o < n_out) {
+    const uint32_t w = o / per_win_out, r = o % per_win_out;
+    const XYZZ<F>* base = in + (size_t)w * win_stride + (size_t)r * base_mul;
+    for (uint32_t j = l; j < len; j += tpo) acc.add(base[(size_t)j * stride]);
   }
-  if (seg) {
-    uint32_t k = seg * L;
-    acc.add(running.mul_u32(&k, 1));
+  for (uint32_t sft = tpo >> 1; sft > 0; sft >>= 1) {
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    if (l < sft) acc.add(sm[threadIdx.x + sft]);
+    __syncthreads();
   }
-  out[t] = acc;
+  if (l == 0 && o < n_out) out[o] = acc;
 }
 
-// out[g] = sum_{j<R} in[g*R + j]   (g < ngroups)
-template <class F>
-__global__ void __launch_bounds__(128) msm_sum_groups(const XYZZ<F>* __restrict__ in, uint32_t R, uint32_t ngroups,
-                                                      XYZZ<F>* __restrict__ out) {
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= ngroups) return;
-  XYZZ<F> acc = in[(size_t)t * R];
-  for (uint32_t j = 1; j < R; j++) acc.add(in[(size_t)t * R + j]);
-  out[t] = acc;
-}
+// Reduction plan for one effective window of 2^m buckets: a binary tree of arrays (node 0 = the buckets).
+static constexpr int MSM_LEAF_LOG = 6;   // arrays of <= 64 points go to the host
+struct MsmRedNode {
+  int log_len, a0, a1;      // a0 = low bits (row length), a1 = high bits (column length)
+  int child_r, child_c;     // -1 for leaves
+  size_t off;               // offset (points, per window) in the device scratch; leaves: offset in the leaf region
+  bool leaf;
+};
+struct MsmRedPlan {
+  MsmRedNode nodes[16];
+  int n_nodes = 0;
+  size_t inner_pts = 0, leaf_pts = 0;   // per window
+  int build(int log_len) {
+    const int id = n_nodes++;
+    MsmRedNode& nd = nodes[id];
+    nd.log_len = log_len;
+    nd.child_r = nd.child_c = -1;
+    nd.leaf = log_len <= MSM_LEAF_LOG;
+    nd.a0 = nd.a1 = 0;
+    nd.off = 0;
+    if (!nd.leaf) {
+      const int a0 = log_len / 2, a1 = log_len - a0;
+      nodes[id].a0 = a0;
+      nodes[id].a1 = a1;
+      const int r = build(a1);
+      const int c = build(a0);
+      nodes[id].child_r = r;
+      nodes[id].child_c = c;
+    }
+    return id;
+  }
+  void layout() {
+    inner_pts = leaf_pts = 0;
+    for (int i = 1; i < n_nodes; i++)
+      if (!nodes[i].leaf) { nodes[i].off = inner_pts; inner_pts += (size_t)1 << nodes[i].log_len; }
+    for (int i = 0; i < n_nodes; i++)
+      if (nodes[i].leaf) { nodes[i].off = leaf_pts; leaf_pts += (size_t)1 << nodes[i].log_len; }
+  }
+  void make(int m) { n_nodes = 0; build(m); layout(); }
+};
 
 // infinity mask of a base array (x == y == 0), computed once when a query is made resident
 template <class F>
@@ -431,26 +484,19 @@ struct DevBuf {
 static constexpr int MSM_K0 = 64;      // sorted entries per thread, level 0
 static constexpr int MSM_KF = 4;       // partial slots per thread, levels >= 1
 static constexpr int MSM_TAIL_S = 2048;  // partial-list length at which the remaining levels fuse into one block
-static constexpr int MSM_GRP = 8;      // fan-in of the window-sum tree
-
-inline uint32_t msm_seg_len(const MsmGeom& g) {
-  // buckets per thread in the bucket reduction: keep >= ~8k threads in flight, at most 16 buckets per thread
-  uint32_t L = 16;
-  while (L > 2 && (uint64_t)g.ne * (g.B / L) < 8192) L >>= 1;
-  if (L > g.B) L = g.B;
-  return L;
-}
 
 template <class F>
 struct MsmWorkspace {
-  DevBuf counters, offsets, blocktot, sidx, skey, buckets, pk0, pp0, pk1, pp1, seg0, seg1;
-  XYZZ<F>* h_winsums = nullptr;  // pinned host staging for the window sums
-  int h_cap = 0;
+  DevBuf counters, offsets, blocktot, sidx, skey, buckets, pk0, pp0, pk1, pp1, pending, red_inner, red_leaf;
+  MsmRedPlan plan;
+  int plan_m = -1, plan_ne = 0;
+  XYZZ<F>* h_leaf = nullptr;  // pinned host copy of the leaf arrays: [node][window][element]
+  size_t h_cap = 0;
   cudaError_t prepare(const MsmGeom& g) {
     cudaError_t e;
     const uint64_t T0 = (g.max_entries + MSM_K0 - 1) / MSM_K0;
     const uint64_t S1 = 2 * T0;
-    const uint64_t T1 = (S1 + MSM_KF - 1) / MSM_KF;
+    const uint64_t T1 = msm_level_threads(S1, MSM_KF);
     const uint64_t S2 = 2 * T1;
 #define G16_TRY(x) if ((e = (x)) != cudaSuccess) return e
     G16_TRY(counters.reserve((size_t)(g.nkeys + 1) * 4));
@@ -463,24 +509,29 @@ struct MsmWorkspace {
     G16_TRY(pp0.reserve(S1 * sizeof(XYZZ<F>)));
     G16_TRY(pk1.reserve(S2 * 4 + 16));
     G16_TRY(pp1.reserve(S2 * sizeof(XYZZ<F>)));
-    const uint32_t L = msm_seg_len(g);
-    const uint64_t nsegs = (uint64_t)g.ne * (g.B / L);
-    G16_TRY(seg0.reserve(nsegs * sizeof(XYZZ<F>)));
-    G16_TRY(seg1.reserve((nsegs / 2 + g.ne) * sizeof(XYZZ<F>)));
-    if (h_cap < g.ne) {
-      if (h_winsums) cudaFreeHost(h_winsums);
-      h_winsums = nullptr;
-      G16_TRY(cudaMallocHost(&h_winsums, (size_t)g.ne * sizeof(XYZZ<F>)));
-      h_cap = g.ne;
+    G16_TRY(pending.reserve(64 * 4));
+    if (plan_m != g.c - 1 || plan_ne != g.ne) {
+      plan.make(g.c - 1);
+      plan_m = g.c - 1;
+      plan_ne = g.ne;
+    }
+    G16_TRY(red_inner.reserve((plan.inner_pts * g.ne + 1) * sizeof(XYZZ<F>)));
+    G16_TRY(red_leaf.reserve((plan.leaf_pts * g.ne + 1) * sizeof(XYZZ<F>)));
+    const size_t need = plan.leaf_pts * g.ne;
+    if (h_cap < need) {
+      if (h_leaf) cudaFreeHost(h_leaf);
+      h_leaf = nullptr;
+      G16_TRY(cudaMallocHost(&h_leaf, need * sizeof(XYZZ<F>)));
+      h_cap = need;
     }
 #undef G16_TRY
     return cudaSuccess;
   }
   void release() {
     counters.release(); offsets.release(); blocktot.release(); sidx.release(); skey.release(); buckets.release();
-    pk0.release(); pp0.release(); pk1.release(); pp1.release(); seg0.release(); seg1.release();
-    if (h_winsums) cudaFreeHost(h_winsums);
-    h_winsums = nullptr;
+    pk0.release(); pp0.release(); pk1.release(); pp1.release(); pending.release(); red_inner.release(); red_leaf.release();
+    if (h_leaf) cudaFreeHost(h_leaf);
+    h_leaf = nullptr;
     h_cap = 0;
   }
 };
@@ -490,11 +541,11 @@ struct MsmCounters {  // launch bookkeeping for bench.py's gpu_launches
 };
 
 // Enqueue one MSM on `st`.  d_bases holds g.copies * g.n affine points (copy-major); d_scalars / d_skip are device
-// pointers; the g.ne window sums land in ws.h_winsums once the stream is synchronised (msm_finish: host Horner).
+// pointers; the leaf arrays of the bucket reduction land in ws.h_leaf once the stream is synchronised (msm_finish).
 template <class F, class FrF>
 cudaError_t msm_enqueue(cudaStream_t st, MsmWorkspace<F>& ws, const MsmGeom& g, const Affine<F>* d_bases,
                         const uint8_t* d_skip, const uint32_t* d_scalars, bool scalars_mont, MsmCounters* ctr,
-                        cudaEvent_t ev_acc0 = nullptr, cudaEvent_t ev_acc1 = nullptr) {
+                        cudaEvent_t ev_acc0, cudaEvent_t ev_acc1) {
   cudaError_t e;
   if (g.n == 0) return cudaSuccess;
   if ((e = ws.prepare(g)) != cudaSuccess) return e;
@@ -503,9 +554,11 @@ cudaError_t msm_enqueue(cudaStream_t st, MsmWorkspace<F>& ws, const MsmGeom& g, 
   uint32_t* blocktot = ws.blocktot.template as<uint32_t>();
   uint32_t* sidx = ws.sidx.template as<uint32_t>();
   uint32_t* skey = ws.skey.template as<uint32_t>();
+  uint32_t* pending = ws.pending.template as<uint32_t>();
   XYZZ<F>* buckets = ws.buckets.template as<XYZZ<F>>();
   unsigned long long nl = 0;
   cudaMemsetAsync(counters, 0, (size_t)(g.nkeys + 1) * 4, st);
+  cudaMemsetAsync(pending, 0, 64 * 4, st);
   cudaMemsetAsync(buckets, 0, (size_t)g.nkeys * sizeof(XYZZ<F>), st);
   const uint32_t nb = (g.n + 255) / 256;
   msm_digits<FrF, false><<<nb, 256, 0, st>>>(d_scalars, scalars_mont ? 1 : 0, d_skip, g, counters, nullptr, nullptr);
@@ -520,55 +573,102 @@ cudaError_t msm_enqueue(cudaStream_t st, MsmWorkspace<F>& ws, const MsmGeom& g, 
   uint32_t* kk[2] = {ws.pk0.template as<uint32_t>(), ws.pk1.template as<uint32_t>()};
   XYZZ<F>* pp[2] = {ws.pp0.template as<XYZZ<F>>(), ws.pp1.template as<XYZZ<F>>()};
   if (ev_acc0) cudaEventRecord(ev_acc0, st);
-  msm_accum_l0<F, MSM_K0><<<(unsigned)((T0 + 127) / 128), 128, 0, st>>>(d_bases, sidx, skey, offsets + g.nkeys, T0, buckets, kk[0], pp[0]);
+  msm_accum_l0<F, MSM_K0><<<(unsigned)((T0 + 127) / 128), 128, 0, st>>>(d_bases, sidx, skey, offsets + g.nkeys, T0, buckets, kk[0], pp[0], pending);
   if (ev_acc1) cudaEventRecord(ev_acc1, st);
   nl += 1;
-  // levels >= 1: ping-pong between the two partial buffers, then one fused tail
+  // levels >= 1: ping-pong between the two partial buffers, then one fused tail; empty levels return immediately
   uint64_t S = 2 * T0;
-  int cur = 0;
-  while (S > (uint64_t)MSM_TAIL_S) {
-    const uint64_t T = (S + MSM_KF - 1) / MSM_KF;
-    msm_accum_ln<F, MSM_KF><<<(unsigned)((T + 127) / 128), 128, 0, st>>>(kk[cur], pp[cur], S, T, buckets, kk[cur ^ 1], pp[cur ^ 1]);
+  int cur = 0, lvl = 0;
+  while (S > (uint64_t)MSM_TAIL_S && lvl < 60) {
+    const uint64_t T = msm_level_threads(S, MSM_KF);
+    msm_accum_ln<F, MSM_KF><<<(unsigned)((T + 127) / 128), 128, 0, st>>>(kk[cur], pp[cur], S, T, buckets, kk[cur ^ 1], pp[cur ^ 1], pending + lvl);
     nl += 1;
     S = 2 * T;
     cur ^= 1;
+    lvl++;
   }
-  msm_accum_tail<F, MSM_KF><<<1, 256, 0, st>>>(kk[cur], pp[cur], kk[cur ^ 1], pp[cur ^ 1], S, buckets);
+  msm_accum_tail<F, MSM_KF><<<1, 256, 0, st>>>(kk[cur], pp[cur], kk[cur ^ 1], pp[cur ^ 1], S, buckets, pending + lvl);
   nl += 1;
-  // bucket reduction
-  const uint32_t L = msm_seg_len(g);
-  uint32_t per_win = g.B / L;
-  const uint32_t nsegs = (uint32_t)g.ne * per_win;
-  XYZZ<F>* a = ws.seg0.template as<XYZZ<F>>();
-  XYZZ<F>* b = ws.seg1.template as<XYZZ<F>>();
-  msm_bucket_reduce<F><<<(nsegs + 127) / 128, 128, 0, st>>>(buckets, g.B, L, nsegs, a);
-  nl += 1;
-  while (per_win > 1) {
-    const uint32_t R = per_win < (uint32_t)MSM_GRP ? per_win : (uint32_t)MSM_GRP;   // per_win is a power of two
-    const uint32_t ng = (uint32_t)g.ne * (per_win / R);
-    msm_sum_groups<F><<<(ng + 127) / 128, 128, 0, st>>>(a, R, ng, b);
-    nl += 1;
-    XYZZ<F>* t = a; a = b; b = t;
-    per_win /= R;
+  // bucket reduction: row / column sums down the plan, leaves to the host
+  constexpr int TPB = sizeof(XYZZ<F>) > 192 ? 64 : 128;
+  const MsmRedPlan& pl = ws.plan;
+  XYZZ<F>* inner = ws.red_inner.template as<XYZZ<F>>();
+  XYZZ<F>* leaf = ws.red_leaf.template as<XYZZ<F>>();
+  auto arr = [&](int id) -> XYZZ<F>* {
+    if (id == 0) return buckets;
+    const MsmRedNode& nd = pl.nodes[id];
+    return (nd.leaf ? leaf : inner) + nd.off * g.ne;
+  };
+  for (int id = 0; id < pl.n_nodes; id++) {   // parents precede children in the node array
+    const MsmRedNode& nd = pl.nodes[id];
+    if (nd.leaf) continue;
+    const uint32_t win_stride = 1u << nd.log_len;
+    for (int side = 0; side < 2; side++) {
+      const bool rows = side == 0;
+      const uint32_t per_win_out = rows ? (1u << nd.a1) : (1u << nd.a0);
+      const uint32_t len = rows ? (1u << nd.a0) : (1u << nd.a1);
+      const uint32_t stride = rows ? 1u : (1u << nd.a0);
+      const uint32_t base_mul = rows ? (1u << nd.a0) : 1u;
+      const uint32_t n_out = per_win_out * (uint32_t)g.ne;
+      uint32_t tpo = TPB;
+      while (tpo > len) tpo >>= 1;
+      const uint32_t opb = TPB / tpo;
+      msm_sum_strided<F, TPB><<<(n_out + opb - 1) / opb, TPB, 0, st>>>(arr(id), arr(rows ? nd.child_r : nd.child_c), n_out, per_win_out,
+                                                                      win_stride, len, stride, base_mul, tpo);
+      nl += 1;
+    }
   }
   if (ctr) ctr->launches += nl;
-  e = cudaMemcpyAsync(ws.h_winsums, a, (size_t)g.ne * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, st);
+  const XYZZ<F>* leaf_src = pl.nodes[0].leaf ? buckets : leaf;
+  e = cudaMemcpyAsync(ws.h_leaf, leaf_src, pl.leaf_pts * g.ne * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, st);
   if (e != cudaSuccess) return e;
   return cudaGetLastError();
 }
 
-// Host Horner over the effective-window sums (stream must be synchronised): sum_e 2^(c e) S_e.
+// Host end of the bucket reduction (stream must be synchronised): weighted sums of the leaf arrays, recombination up
+// the plan, then Horner over the effective windows: sum_e 2^(c e) S_e.
+template <class F>
+struct MsmHostRed {
+  const MsmWorkspace<F>& ws;
+  const MsmGeom& g;
+  int w;
+  // returns T(node) = sum_i (i + 1) X_i and sets total = sum_i X_i
+  XYZZ<F> T(int id, XYZZ<F>& total) const {
+    const MsmRedNode& nd = ws.plan.nodes[id];
+    if (nd.leaf) {
+      const size_t len = (size_t)1 << nd.log_len;
+      const XYZZ<F>* x = ws.h_leaf + nd.off * g.ne + (size_t)w * len;
+      XYZZ<F> running = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
+      for (size_t i = len; i-- > 0;) {
+        running.add(x[i]);
+        acc.add(running);
+      }
+      total = running;
+      return acc;
+    }
+    XYZZ<F> tot_r, tot_c;
+    XYZZ<F> tr = T(nd.child_r, tot_r);   // sum (hi + 1) R_hi
+    XYZZ<F> tc = T(nd.child_c, tot_c);   // sum (lo + 1) C_lo
+    tot_r.negate();
+    tr.add(tot_r);                       // sum hi R_hi
+    for (int k = 0; k < nd.a0; k++) tr.dbl_inplace();
+    tr.add(tc);
+    total = tot_c;
+    return tr;
+  }
+};
 template <class F>
 XYZZ<F> msm_finish(const MsmWorkspace<F>& ws, const MsmGeom& g) {
   XYZZ<F> acc = XYZZ<F>::inf();
   if (g.n == 0) return acc;
   for (int w = g.ne - 1; w >= 0; w--) {
     for (int k = 0; k < g.c; k++) acc.dbl_inplace();
-    acc.add(ws.h_winsums[w]);
+    MsmHostRed<F> hr{ws, g, w};
+    XYZZ<F> tot;
+    acc.add(hr.T(0, tot));
   }
   return acc;
 }
-
 
 // Make a query resident: identity mask of copy 0 and (copies > 1) the precomputed multiples 2^(shift*j) * P.
 template <class F>

@@ -233,3 +233,70 @@ def test_sharded_prove_equals_single():
     want = P.proof_in_the_exponent(opk, cs, r_, s_)
     pf = proof_from_abi(curve, sharded)
     assert (pf.a, pf.b, pf.c) == (want.a, want.b, want.c)
+
+
+def _oracle_vs_gpu(curve, m, z, flags=0):
+    """full prove through the C ABI vs the C++ CPU oracle on the same (pk, matrices, assignment, r, s)"""
+    import orc
+    from groth16_b200.params import GENERATORS
+    c = P.CURVES[curve]
+    g = engine(curve)
+    cd = g.codec
+    G = GENERATORS[curve]
+    pk = g.generate_parameters_with_qap(m, 11, 22, 33, 44, 55, G["g1"], G["g2"])
+    r, s = cd.fr.enc1(123456789), cd.fr.enc1(987654321)
+    got = g.create_proof_with_reduction_and_matrices(None, r, s, None, m.num_instance_variables, m.num_constraints, z, flags=flags)
+    want, _ = orc.prove(c.cid, cd.nq, pk, m, z, r, s, threads=8)
+    nq = cd.nq
+    assert np.array_equal(got.a, want[:2 * nq]) and np.array_equal(got.b, want[2 * nq:6 * nq]) and np.array_equal(got.c, want[6 * nq:])
+    return pk, got
+
+
+@pytest.mark.parametrize("curve", ALL_CURVES)
+def test_prove_dummy_circuit_degenerate_distribution(curve):
+    """benches/bench.rs:41-64 DummyCircuit: every witness scalar equal (each MSM window hits ONE bucket: maximal skew),
+    a/b queries almost all identity.  2^12 - 100 constraints; proof bit-exact with the CPU oracle and pairing-verified."""
+    from groth16_b200.workload import dummy_r1cs
+    m, z, pub = dummy_r1cs(curve, (1 << 12) - 100, (1 << 12) - 100)
+    pk_abi, got = _oracle_vs_gpu(curve, m, z)
+    opk = pk_from_abi(curve, pk_abi)
+    assert P.verify_proof(opk.vk, P.CURVES[curve], proof_from_abi(curve, got), pub)
+
+
+@pytest.mark.parametrize("curve", ALL_CURVES)
+def test_prove_synthetic_2p14(curve):
+    """Non-degenerate synthetic R1CS at 2^14 (multi-pass NTT, precomputed-multiple MSM path) vs the CPU oracle, concurrent
+    and serialised stream schedules; witness map alone vs the oracle as well."""
+    import orc
+    from groth16_b200 import _lib
+    from groth16_b200.workload import synthetic_r1cs
+    m, z, pub = synthetic_r1cs(curve, 14, seed=5)
+    _oracle_vs_gpu(curve, m, z)
+    _oracle_vs_gpu(curve, m, z, flags=_lib.SERIAL_MSMS)
+    g = engine(curve)
+    h = g.witness_map_from_matrices(None, m.num_instance_variables, m.num_constraints, z)
+    assert np.array_equal(h, orc.witness_map(P.CURVES[curve].cid, m, z, threads=8))
+
+
+def test_msm_skewed_scalars_large():
+    """2^15-point G1 MSM whose scalars are 50 % in {0,1}, 25 % < 2^32, 25 % uniform (SURVEY.md section 8d 'realistic mix'):
+    giant buckets exercise every level of the segmented reduction.  Checked against the CPU oracle."""
+    import orc
+    curve = "bls12_381"
+    c = P.CURVES[curve]
+    g = engine(curve)
+    cd = g.codec
+    n = 1 << 15
+    rs = np.random.RandomState(3)
+    from groth16_b200.params import GENERATORS
+    ks = rs.randint(0, 1 << 62, size=(n, 4), dtype=np.int64).astype(np.uint64)
+    ks[:, 3] &= np.uint64((1 << 58) - 1)
+    bases = orc.batch_mul_g1(c.cid, cd.nq, cd.enc_g1([GENERATORS[curve]["g1"]])[0], ks, threads=8)
+    sc = rs.randint(0, 1 << 62, size=(n, 4), dtype=np.int64).astype(np.uint64)
+    sc[:, 3] &= np.uint64((1 << 58) - 1)
+    kind = rs.randint(0, 4, size=n)
+    sc[kind <= 1] = 0
+    sc[kind <= 1, 0] = rs.randint(0, 2, size=int((kind <= 1).sum())).astype(np.uint64)
+    sc[kind == 2, 1:] = 0
+    sc[kind == 2, 0] &= np.uint64(0xFFFFFFFF)
+    assert np.array_equal(g.msm_g1(bases, sc), orc.msm_g1(c.cid, cd.nq, bases, sc, threads=8))

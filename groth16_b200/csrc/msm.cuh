@@ -228,8 +228,13 @@ __device__ __forceinline__ Affine<F> load_affine(const Affine<F>* __restrict__ b
 }
 
 // Level 0: grid covers T0 = ceil(max_entries / K0) threads; threads past the real entry count only clear their slots.
+// Register budget: 3 resident blocks per SM for single-field points (G1), 2 for Fq2 points (G2).  (Staging the gathered
+// bases through shared memory with cp.async was measured and is slower: with 3 warps per scheduler the gather latency
+// is already hidden and the kernel is bound by the IMAD.WIDE pipe, profiles/.)
+template <class F>
+struct MsmAccumCfg { static constexpr int MIN_BLOCKS = sizeof(F) <= 48 ? 3 : 2; };
 template <class F, int K0>
-__global__ void __launch_bounds__(128) msm_accum_l0(const Affine<F>* __restrict__ bases,
+__global__ void __launch_bounds__(128, MsmAccumCfg<F>::MIN_BLOCKS) msm_accum_l0(const Affine<F>* __restrict__ bases,
                                                     const uint32_t* __restrict__ sidx,
                                                     const uint32_t* __restrict__ skey,
                                                     const uint32_t* __restrict__ total_ptr, uint64_t T0,

@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstdio>
 #include <string>
+#include <thread>
 #include <vector>
 #include "../../include/g16b200.h"
 #include "ec.cuh"
@@ -99,9 +100,12 @@ struct Engine : IEngine {
   int cfg_maxcopies = MSM_MAX_COPIES;
   MsmGeom pick_geom(uint64_t cnt) const {
     if (cfg_ne <= 0) return msm_geom(cnt, FR_BITS, cfg_c, 0);
-    MsmGeom g = msm_geom(cnt, FR_BITS, cfg_c, cfg_ne);
+    // with all windows sharing one bucket set the bucket count is 2^(c-1) whatever the size: c = 16 from 2^16 pairs up
+    // (also for the per-rank shards of a multi-GPU run), the size-based rule below that
+    const int c = cfg_c > 0 ? cfg_c : (cnt >= (1u << 16) ? 16 : 0);
+    MsmGeom g = msm_geom(cnt, FR_BITS, c, cfg_ne);
     int ne = cfg_ne;
-    while (g.copies > cfg_maxcopies) g = msm_geom(cnt, FR_BITS, cfg_c, ++ne);
+    while (g.copies > cfg_maxcopies) g = msm_geom(cnt, FR_BITS, c, ++ne);
     return g;
   }
   template <class F>
@@ -594,29 +598,29 @@ struct Engine : IEngine {
       }
       G16_CUDA(cudaEventRecord(ev_m1[m], st));
     }
-    // Finish each MSM on the host as soon as its stream drains, in expected completion order (B2 has the highest stream
-    // priority, L / A / B1 the lowest), so that the host-side leaf sums overlap the GPU work still in flight.
-    float host_ms = 0;
-    auto finish1 = [&](int m, P1& dst) -> int {
-      if (!serial) G16_CUDA(cudaStreamSynchronize(st_msm[m]));
-      auto t0 = std::chrono::steady_clock::now();
-      dst = run[m] ? msm_finish<Fq>(ws1[m], geom[m]) : P1::inf();
-      host_ms += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
-      return G16_OK;
-    };
+    // Finish each MSM on the host (leaf sums of the bucket reduction, Horner) as soon as its stream drains, one host
+    // thread per MSM: the host work of the early finishers overlaps the GPU work still in flight.
     if (serial) G16_CUDA(cudaStreamSynchronize(st_main));
     {
-      if (!serial) G16_CUDA(cudaStreamSynchronize(st_msm[M_B2]));
       auto t0 = std::chrono::steady_clock::now();
-      out.b2 = run[M_B2] ? msm_finish<Fq2>(ws2, geom[M_B2]) : P2::inf();
-      host_ms += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      cudaError_t errs[5] = {cudaSuccess, cudaSuccess, cudaSuccess, cudaSuccess, cudaSuccess};
+      P1* outs1[4] = {&out.h, &out.l, &out.a, &out.b1};
+      std::thread th[5];
+      for (int m = 0; m < 5; m++) {
+        th[m] = std::thread([&, m]() {
+          cudaSetDevice(device);
+          if (!serial) errs[m] = cudaStreamSynchronize(st_msm[m]);
+          if (errs[m] != cudaSuccess) return;
+          if (m == M_B2) out.b2 = run[m] ? msm_finish<Fq2>(ws2, geom[m]) : P2::inf();
+          else *outs1[m] = run[m] ? msm_finish<Fq>(ws1[m], geom[m]) : P1::inf();
+        });
+      }
+      for (auto& t : th) t.join();
+      for (int m = 0; m < 5; m++)
+        if (errs[m] != cudaSuccess) return fail(G16_ERR_CUDA, std::string("msm stream sync: ") + cudaGetErrorString(errs[m]));
+      G16_CUDA(cudaStreamSynchronize(st_main));
+      tm.host_finish_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     }
-    if ((rc = finish1(M_H, out.h))) return rc;
-    if ((rc = finish1(M_L, out.l))) return rc;
-    if ((rc = finish1(M_A, out.a))) return rc;
-    if ((rc = finish1(M_B1, out.b1))) return rc;
-    G16_CUDA(cudaStreamSynchronize(st_main));
-    tm.host_finish_ms = host_ms;
     // timings
     float ms = 0, tot = 0;
     cudaEventElapsedTime(&tm.h2d_ms, ev_start, ev_z);
@@ -651,36 +655,49 @@ struct Engine : IEngine {
     store_partials(partial, x);
     return G16_OK;
   }
-  // prover.rs:76-131 on the host, from the five MSM sums
-  int assemble(const Fr& r, const Fr& s, const Partials& x, uint64_t* proof) {
+  // prover.rs:76-131 on the host.  The four scalar multiplications that depend only on (r, s) and the key are computed
+  // by a helper thread while the GPU works (fixed_muls); the two that need MSM results follow in assemble().
+  struct FixedMuls { P1 r_d1, s_d1, rs_d1; P2 s_d2; };
+  FixedMuls fixed_muls(const Fr& r, const Fr& s) const {
     uint32_t rk[8], sk[8], rsk[8];
     fr_to_canon(r, rk);
     fr_to_canon(s, sk);
     fr_to_canon(Fr::mul(r, s), rsk);
     const P1 d1 = P1::from_affine(delta_g1);
-    P1 r_s_delta_g1 = d1.mul_u32(rsk, 8);                 // prover.rs:76
+    FixedMuls f;
+    f.rs_d1 = d1.mul_u32(rsk, 8);                          // prover.rs:76
+    f.r_d1 = d1.mul_u32(rk, 8);                            // prover.rs:90
+    f.s_d1 = r.is_zero() ? P1::inf() : d1.mul_u32(sk, 8);  // prover.rs:100
+    f.s_d2 = P2::from_affine(delta_g2).mul_u32(sk, 8);     // prover.rs:112
+    return f;
+  }
+  int assemble(const Fr& r, const Fr& s, const Partials& x, const FixedMuls& f, uint64_t* proof) {
+    uint32_t rk[8], sk[8];
+    fr_to_canon(r, rk);
+    fr_to_canon(s, sk);
     // g_a = r*delta_g1 + a_query[0] + msm + alpha_g1         prover.rs:90-92,252-270
-    P1 g_a = d1.mul_u32(rk, 8);
+    P1 g_a = f.r_d1;
     g_a.madd(a0);
     g_a.add(x.a);
     g_a.madd(alpha_g1);
     P1 s_g_a = g_a.mul_u32(sk, 8);                        // prover.rs:94
     P1 g1_b = P1::inf();
     if (!r.is_zero()) {                                   // prover.rs:98-108
-      g1_b = d1.mul_u32(sk, 8);
+      g1_b = f.s_d1;
       g1_b.madd(b1_0);
       g1_b.add(x.b1);
       g1_b.madd(beta_g1);
     }
-    P2 g2_b = P2::from_affine(delta_g2).mul_u32(sk, 8);   // prover.rs:112-113
+    P2 g2_b = f.s_d2;                                     // prover.rs:112-113
     g2_b.madd(b2_0);
     g2_b.add(x.b2);
     g2_b.madd(beta_g2);
     P1 r_g1_b = g1_b.mul_u32(rk, 8);                      // prover.rs:114
     P1 g_c = s_g_a;                                       // prover.rs:119-124
     g_c.add(r_g1_b);
-    r_s_delta_g1.negate();
-    g_c.add(r_s_delta_g1);
+    P1 neg_rsd = f.rs_d1;
+    neg_rsd.negate();
+    g_c.add(neg_rsd);
     g_c.add(x.l);
     g_c.add(x.h);
     store_a1(proof, g_a.to_affine());                     // prover.rs:127-131
@@ -691,11 +708,16 @@ struct Engine : IEngine {
   int prove(const uint64_t* r, const uint64_t* s, const uint64_t* z, uint32_t flags, uint64_t* proof) override {
     if (!s || !proof) return fail(G16_ERR_BAD_ARGUMENT, "null buffer");
     if (world != 1) return fail(G16_ERR_BAD_ARGUMENT, "key is sharded: use g16_prove_partial + g16_prove_assemble");
+    if (!r) return fail(G16_ERR_BAD_ARGUMENT, "null buffer");
     Partials x;
+    const Fr rr = load_fr(r), ss = load_fr(s);
+    FixedMuls fx;
+    std::thread helper([&]() { fx = fixed_muls(rr, ss); });
     int rc = run_msms(r, z, flags, x);
+    helper.join();
     if (rc) return rc;
     auto t0 = std::chrono::steady_clock::now();
-    rc = assemble(load_fr(r), load_fr(s), x, proof);
+    rc = assemble(rr, ss, x, fx, proof);
     tm.host_finish_ms += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     tm.d2h_bytes += 8 * NQ64 * 8;
     return rc;
@@ -713,7 +735,8 @@ struct Engine : IEngine {
       x.b1.madd(load_a1(p + 6 * NQ64));
       x.b2.madd(load_a2(p + 8 * NQ64));
     }
-    return assemble(load_fr(r), load_fr(s), x, proof);
+    const Fr rr = load_fr(r), ss = load_fr(s);
+    return assemble(rr, ss, x, fixed_muls(rr, ss), proof);
   }
 };
 

@@ -18,6 +18,7 @@
 // benches/bench.rs:43-54) cost the same as uniform ones: work is split by sorted position, not by bucket.
 #pragma once
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include "ec.cuh"
 
 namespace g16 {
@@ -230,7 +231,8 @@ __device__ __forceinline__ Affine<F> load_affine(const Affine<F>* __restrict__ b
 // Level 0: grid covers T0 = ceil(max_entries / K0) threads; threads past the real entry count only clear their slots.
 // Register budget: 3 resident blocks per SM for single-field points (G1), 2 for Fq2 points (G2).  (Staging the gathered
 // bases through shared memory with cp.async was measured and is slower: with 3 warps per scheduler the gather latency
-// is already hidden and the kernel is bound by the IMAD.WIDE pipe, profiles/.)
+// is already hidden and the kernel is bound by the IMAD.WIDE pipe, profiles/.  Also measured and slower: the running sum
+// kept in shared memory for one more resident block per SM; lazily reduced double-width products.)
 template <class F>
 struct MsmAccumCfg { static constexpr int MIN_BLOCKS = sizeof(F) <= 48 ? 3 : 2; };
 template <class F, int K0>

@@ -300,3 +300,41 @@ def test_msm_skewed_scalars_large():
     sc[kind == 2, 1:] = 0
     sc[kind == 2, 0] &= np.uint64(0xFFFFFFFF)
     assert np.array_equal(g.msm_g1(bases, sc), orc.msm_g1(c.cid, cd.nq, bases, sc, threads=8))
+
+
+def test_api_error_paths():
+    """Status codes instead of panics across the ABI (Cargo.toml:61 panic='abort' rationale): wrong order of calls, bad
+    indices, sharded key used with the single-GPU entry point, domain larger than the field's two-adicity."""
+    from groth16_b200 import ConstraintMatrices, PolynomialDegreeTooLarge
+    g = Groth16("bn254", 0)
+    c = P.CURVES["bn254"]
+    cs = P.silly_circuit(c, 3, 5)
+    m = matrices_from_r1cs(cs)
+    z = g.codec.fr.enc(cs.assignment)
+    with pytest.raises(ValueError):      # no circuit / key resident yet
+        g.create_proof_with_reduction_and_matrices(None, 1, 2, None, 2, 6, z)
+    opk = pk_to_abi(P.generate_parameters(cs, *toxic(c, 1)))
+    with pytest.raises(ValueError):      # g16_pk_load before g16_circuit_load
+        g.load_proving_key(opk)
+    bad = ConstraintMatrices(m.num_instance_variables, m.num_witness_variables, m.num_constraints,
+                             (m.a[0], m.a[1] + 100, m.a[2]), m.b, m.c)
+    with pytest.raises(ValueError):      # column index out of range
+        g.load_matrices(bad)
+    g.load_matrices(m)
+    g.load_proving_key(opk, 0, 2)        # sharded residency
+    with pytest.raises(ValueError):
+        g.create_proof_with_reduction_and_matrices(None, 1, 2, None, 2, 6, z)
+    g.load_proving_key(opk)
+    with pytest.raises(ValueError):      # wrong assignment length
+        g.create_proof_with_reduction_and_matrices(None, 1, 2, None, 2, 6, z[:-1])
+    pf = g.create_proof_with_reduction_and_matrices(None, 1, 2, None, 2, 6, z)
+    want = P.create_proof(P.generate_parameters(cs, *toxic(c, 1)), cs, 1, 2)
+    got = proof_from_abi("bn254", pf)
+    assert (got.a, got.b, got.c) == (want.a, want.b, want.c)
+    # a circuit whose domain would exceed 2^28 on BN254 -> PolynomialDegreeTooLarge (r1cs_to_qap.rs:178-179)
+    rp = np.zeros(2, dtype=np.uint32)
+    empty = (rp, np.zeros(0, dtype=np.uint32), np.zeros((0, 4), dtype=np.uint64))
+    huge = ConstraintMatrices((1 << 28) + 1, 1, 1, empty, empty, empty)
+    with pytest.raises(PolynomialDegreeTooLarge):
+        g.load_matrices(huge)
+    g.close()

@@ -108,6 +108,12 @@ struct Engine : IEngine {
     while (g.copies > cfg_maxcopies) g = msm_geom(cnt, FR_BITS, c, ++ne);
     return g;
   }
+  // entries per level-0 thread, from the number of resident accumulation threads of this device
+  int sm_count = 148;
+  MsmGeom with_k0(MsmGeom g, bool g2) const {
+    g.k0 = msm_pick_k0(g.max_entries, (uint64_t)sm_count * 128 * (g2 ? 2 : 3));
+    return g;
+  }
   template <class F>
   int finish_query(Query& x) {   // x.bases holds copy 0; build the other copies and the infinity mask
     const uint64_t cnt = x.hi - x.lo;
@@ -131,6 +137,7 @@ struct Engine : IEngine {
     cudaDeviceProp prop;
     G16_CUDA(cudaGetDeviceProperties(&prop, dev));
     if (prop.major < 10) return fail(G16_ERR_CUDA, "device is not sm_100-class (this library ships sm_100a code only)");
+    sm_count = prop.multiProcessorCount;
     if (const char* v = getenv("G16_MSM_C")) cfg_c = atoi(v);
     if (const char* v = getenv("G16_MSM_NE")) cfg_ne = atoi(v);
     if (const char* v = getenv("G16_MSM_MAXCOPIES")) cfg_maxcopies = std::max(1, std::min(atoi(v), (int)MSM_MAX_COPIES));
@@ -291,7 +298,7 @@ struct Engine : IEngine {
       G16_CUDA(cudaMemcpyAsync(db.p, bases, n * sizeof(Affine<F>), cudaMemcpyHostToDevice, st_main));
       G16_CUDA(cudaMemcpyAsync(ds.p, scalars, n * 32, cudaMemcpyHostToDevice, st_main));
       G16_CUDA(msm_prepare_query<F>(st_main, db.template as<Affine<F>>(), (uint32_t)n, 1, 0, dm.template as<uint8_t>()));
-      const MsmGeom g = msm_geom(n, FR_BITS, cfg_c, 0);   // caller-supplied bases: no precomputed copies
+      const MsmGeom g = with_k0(msm_geom(n, FR_BITS, cfg_c, 0), sizeof(F) > 48);   // caller-supplied bases: no precomputed copies
       cudaError_t e = msm_enqueue<F, Fr>(st_main, ws, g, db.template as<Affine<F>>(), dm.template as<uint8_t>(), ds.template as<uint32_t>(), false, &ctr, nullptr, nullptr);
       if (e != cudaSuccess) { db.release(); ds.release(); dm.release(); return fail(G16_ERR_CUDA, std::string("msm_enqueue: ") + cudaGetErrorString(e)); }
       e = cudaStreamSynchronize(st_main);
@@ -348,7 +355,7 @@ struct Engine : IEngine {
     x.pairs = pairs;
     x.lo = pairs * rank / world;
     x.hi = pairs * (rank + 1) / world;
-    x.geom = pick_geom(x.hi - x.lo);
+    x.geom = with_k0(pick_geom(x.hi - x.lo), &x == &q[M_B2]);
   }
   template <class F>
   int upload_query(Query& x, const uint64_t* host_full, uint64_t skip_first) {

@@ -34,8 +34,17 @@ struct MsmGeom {
   uint32_t B;        // buckets per effective window = 2^(c-1)  (digit magnitudes 1..B)
   uint32_t nkeys;    // ne * B
   uint64_t max_entries;  // n * W
+  int k0;            // sorted entries per thread in the level-0 accumulation (64 for large MSMs, less to fill the GPU)
 };
 
+static constexpr int MSM_K0_MAX = 64;
+// Entries per thread so that the level-0 grid is at least ~2.5 waves of `resident_threads` (small MSMs, e.g. the per-rank
+// shards of a multi-GPU proof, would otherwise run as a fraction of one wave: time = one 64-entry chunk regardless of size).
+inline int msm_pick_k0(uint64_t max_entries, uint64_t resident_threads) {
+  int k0 = MSM_K0_MAX;
+  while (k0 > 8 && max_entries / k0 < resident_threads * 5 / 2) k0 >>= 1;
+  return k0;
+}
 inline int msm_pick_c(uint64_t n) {
   int lg = 0;
   while ((1ull << lg) < n) lg++;
@@ -56,6 +65,7 @@ inline MsmGeom msm_geom(uint64_t n, int scalar_bits, int c_override = 0, int ne_
   g.B = 1u << (g.c - 1);
   g.nkeys = (uint32_t)g.ne * g.B;
   g.max_entries = (uint64_t)n * g.W;
+  g.k0 = MSM_K0_MAX;
   return g;
 }
 
@@ -235,11 +245,11 @@ __device__ __forceinline__ Affine<F> load_affine(const Affine<F>* __restrict__ b
 // kept in shared memory for one more resident block per SM; lazily reduced double-width products.)
 template <class F>
 struct MsmAccumCfg { static constexpr int MIN_BLOCKS = sizeof(F) <= 48 ? 3 : 2; };
-template <class F, int K0>
+template <class F>
 __global__ void __launch_bounds__(128, MsmAccumCfg<F>::MIN_BLOCKS) msm_accum_l0(const Affine<F>* __restrict__ bases,
                                                     const uint32_t* __restrict__ sidx,
                                                     const uint32_t* __restrict__ skey,
-                                                    const uint32_t* __restrict__ total_ptr, uint64_t T0,
+                                                    const uint32_t* __restrict__ total_ptr, uint64_t T0, uint32_t K0,
                                                     XYZZ<F>* __restrict__ buckets, uint32_t* __restrict__ okeys,
                                                     XYZZ<F>* __restrict__ opts, uint32_t* pending0) {
   const uint32_t M = *total_ptr;
@@ -247,7 +257,7 @@ __global__ void __launch_bounds__(128, MsmAccumCfg<F>::MIN_BLOCKS) msm_accum_l0(
   if (t == 0) *pending0 = 1;   // level 0 always hands a (possibly empty) partial list to level 1
   if (t >= T0) return;
   MsmEmit<F> em{buckets, okeys, opts, t, false, false};
-  const uint64_t begin = t * K0;
+  const uint64_t begin = t * (uint64_t)K0;
   if (begin >= M) { em.finish(); return; }
   const uint32_t end = (uint32_t)min((uint64_t)M, begin + K0);
   const uint32_t prev = begin > 0 ? skey[begin - 1] : MSM_INVALID;
@@ -255,6 +265,7 @@ __global__ void __launch_bounds__(128, MsmAccumCfg<F>::MIN_BLOCKS) msm_accum_l0(
   uint32_t cur = skey[begin];
   bool first_seg = true;
   XYZZ<F> acc = XYZZ<F>::inf();
+#pragma unroll 1
   for (uint32_t e = (uint32_t)begin; e < end; e++) {
     const uint32_t k = skey[e];
     if (k != cur) {
@@ -355,20 +366,36 @@ __global__ void __launch_bounds__(256) msm_accum_tail(uint32_t* k0, XYZZ<F>* p0,
 // <= 64 points) is finished on the host, where a point addition costs ~0.6 us.  Each bucket enters two additions, like
 // in the classic running-sum trick.
 //
-// out[o] = sum_{j < len} in[w * win_stride + r * base_mul + j * stride],  o = w * per_win_out + r.
-// `tpo` threads cooperate on one output: strided serial part, then a shared-memory tree.
+// job: out[o] = sum_{j < len} in[w * win_stride + r * base_mul + j * stride],  o = w * per_win_out + r.
+// `tpo` threads cooperate on one output: strided serial part, then a shared-memory tree.  Up to 4 independent jobs
+// (the row and the column sums of one or two arrays) share a launch: blocks [first_block, first_block + n_blocks).
+template <class F>
+struct MsmSumJob {
+  const XYZZ<F>* in;
+  XYZZ<F>* out;
+  uint32_t n_out, per_win_out, win_stride, len, stride, base_mul, tpo, first_block;
+};
+template <class F>
+struct MsmSumJobs {
+  MsmSumJob<F> j[4];
+  int n;
+};
 template <class F, int TPB>
-__global__ void __launch_bounds__(TPB) msm_sum_strided(const XYZZ<F>* __restrict__ in, XYZZ<F>* __restrict__ out,
-                                                       uint32_t n_out, uint32_t per_win_out, uint32_t win_stride,
-                                                       uint32_t len, uint32_t stride, uint32_t base_mul, uint32_t tpo) {
+__global__ void __launch_bounds__(TPB) msm_sum_strided(MsmSumJobs<F> jobs) {
   __shared__ XYZZ<F> sm[TPB];
+  int ji = 0;
+#pragma unroll
+  for (int k = 1; k < 4; k++)
+    if (k < jobs.n && blockIdx.x >= jobs.j[k].first_block) ji = k;
+  const MsmSumJob<F>& jb = jobs.j[ji];
+  const uint32_t tpo = jb.tpo;
   const uint32_t g = threadIdx.x / tpo, l = threadIdx.x % tpo;
-  const uint32_t o = blockIdx.x * (TPB / tpo) + g;
+  const uint32_t o = (blockIdx.x - jb.first_block) * (TPB / tpo) + g;
   XYZZ<F> acc = XYZZ<F>::inf();
-  if (o < n_out) {
-    const uint32_t w = o / per_win_out, r = o % per_win_out;
-    const XYZZ<F>* base = in + (size_t)w * win_stride + (size_t)r * base_mul;
-    for (uint32_t j = l; j < len; j += tpo) acc.add(base[(size_t)j * stride]);
+  if (o < jb.n_out) {
+    const uint32_t w = o / jb.per_win_out, r = o % jb.per_win_out;
+    const XYZZ<F>* base = jb.in + (size_t)w * jb.win_stride + (size_t)r * jb.base_mul;
+    for (uint32_t j = l; j < jb.len; j += tpo) acc.add(base[(size_t)j * jb.stride]);
   }
   for (uint32_t sft = tpo >> 1; sft > 0; sft >>= 1) {
     sm[threadIdx.x] = acc;
@@ -376,7 +403,7 @@ __global__ void __launch_bounds__(TPB) msm_sum_strided(const XYZZ<F>* __restrict
     if (l < sft) acc.add(sm[threadIdx.x + sft]);
     __syncthreads();
   }
-  if (l == 0 && o < n_out) out[o] = acc;
+  if (l == 0 && o < jb.n_out) jb.out[o] = acc;
 }
 
 // Reduction plan for one effective window of 2^m buckets: a binary tree of arrays (node 0 = the buckets).
@@ -488,7 +515,6 @@ struct DevBuf {
   T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-static constexpr int MSM_K0 = 64;      // sorted entries per thread, level 0
 static constexpr int MSM_KF = 4;       // partial slots per thread, levels >= 1
 static constexpr int MSM_TAIL_S = 2048;  // partial-list length at which the remaining levels fuse into one block
 
@@ -501,7 +527,7 @@ struct MsmWorkspace {
   size_t h_cap = 0;
   cudaError_t prepare(const MsmGeom& g) {
     cudaError_t e;
-    const uint64_t T0 = (g.max_entries + MSM_K0 - 1) / MSM_K0;
+    const uint64_t T0 = (g.max_entries + g.k0 - 1) / g.k0;
     const uint64_t S1 = 2 * T0;
     const uint64_t T1 = msm_level_threads(S1, MSM_KF);
     const uint64_t S2 = 2 * T1;
@@ -576,11 +602,11 @@ cudaError_t msm_enqueue(cudaStream_t st, MsmWorkspace<F>& ws, const MsmGeom& g, 
   msm_digits<FrF, true><<<nb, 256, 0, st>>>(d_scalars, scalars_mont ? 1 : 0, d_skip, g, counters, sidx, skey);
   nl += 5;
   // level 0
-  const uint64_t T0 = (g.max_entries + MSM_K0 - 1) / MSM_K0;
+  const uint64_t T0 = (g.max_entries + g.k0 - 1) / g.k0;
   uint32_t* kk[2] = {ws.pk0.template as<uint32_t>(), ws.pk1.template as<uint32_t>()};
   XYZZ<F>* pp[2] = {ws.pp0.template as<XYZZ<F>>(), ws.pp1.template as<XYZZ<F>>()};
   if (ev_acc0) cudaEventRecord(ev_acc0, st);
-  msm_accum_l0<F, MSM_K0><<<(unsigned)((T0 + 127) / 128), 128, 0, st>>>(d_bases, sidx, skey, offsets + g.nkeys, T0, buckets, kk[0], pp[0], pending);
+  msm_accum_l0<F><<<(unsigned)((T0 + 127) / 128), 128, 0, st>>>(d_bases, sidx, skey, offsets + g.nkeys, T0, (uint32_t)g.k0, buckets, kk[0], pp[0], pending);
   if (ev_acc1) cudaEventRecord(ev_acc1, st);
   nl += 1;
   // levels >= 1: ping-pong between the two partial buffers, then one fused tail; empty levels return immediately
@@ -606,23 +632,52 @@ cudaError_t msm_enqueue(cudaStream_t st, MsmWorkspace<F>& ws, const MsmGeom& g, 
     const MsmRedNode& nd = pl.nodes[id];
     return (nd.leaf ? leaf : inner) + nd.off * g.ne;
   };
-  for (int id = 0; id < pl.n_nodes; id++) {   // parents precede children in the node array
-    const MsmRedNode& nd = pl.nodes[id];
-    if (nd.leaf) continue;
-    const uint32_t win_stride = 1u << nd.log_len;
-    for (int side = 0; side < 2; side++) {
-      const bool rows = side == 0;
-      const uint32_t per_win_out = rows ? (1u << nd.a1) : (1u << nd.a0);
-      const uint32_t len = rows ? (1u << nd.a0) : (1u << nd.a1);
-      const uint32_t stride = rows ? 1u : (1u << nd.a0);
-      const uint32_t base_mul = rows ? (1u << nd.a0) : 1u;
-      const uint32_t n_out = per_win_out * (uint32_t)g.ne;
-      uint32_t tpo = TPB;
-      while (tpo > len) tpo >>= 1;
-      const uint32_t opb = TPB / tpo;
-      msm_sum_strided<F, TPB><<<(n_out + opb - 1) / opb, TPB, 0, st>>>(arr(id), arr(rows ? nd.child_r : nd.child_c), n_out, per_win_out,
-                                                                      win_stride, len, stride, base_mul, tpo);
-      nl += 1;
+  // one launch per depth of the plan: the row and column sums of every non-leaf node at that depth are independent jobs
+  {
+    int depth_of[16];
+    int max_depth = 0;
+    depth_of[0] = 0;
+    for (int id = 0; id < pl.n_nodes; id++) {   // parents precede children in the node array
+      const MsmRedNode& nd = pl.nodes[id];
+      if (nd.leaf) continue;
+      depth_of[nd.child_r] = depth_of[nd.child_c] = depth_of[id] + 1;
+      if (depth_of[id] > max_depth) max_depth = depth_of[id];
+    }
+    for (int d = 0; d <= max_depth; d++) {
+      MsmSumJobs<F> jobs;
+      jobs.n = 0;
+      uint32_t blocks = 0;
+      auto flush = [&]() {
+        if (jobs.n) {
+          msm_sum_strided<F, TPB><<<blocks, TPB, 0, st>>>(jobs);
+          nl += 1;
+        }
+        jobs.n = 0;
+        blocks = 0;
+      };
+      for (int id = 0; id < pl.n_nodes; id++) {
+        const MsmRedNode& nd = pl.nodes[id];
+        if (nd.leaf || depth_of[id] != d) continue;
+        for (int side = 0; side < 2; side++) {
+          const bool rows = side == 0;
+          MsmSumJob<F>& jb = jobs.j[jobs.n];
+          jb.in = arr(id);
+          jb.out = arr(rows ? nd.child_r : nd.child_c);
+          jb.per_win_out = rows ? (1u << nd.a1) : (1u << nd.a0);
+          jb.win_stride = 1u << nd.log_len;
+          jb.len = rows ? (1u << nd.a0) : (1u << nd.a1);
+          jb.stride = rows ? 1u : (1u << nd.a0);
+          jb.base_mul = rows ? (1u << nd.a0) : 1u;
+          jb.n_out = jb.per_win_out * (uint32_t)g.ne;
+          uint32_t tpo = TPB;
+          while (tpo > jb.len) tpo >>= 1;
+          jb.tpo = tpo;
+          jb.first_block = blocks;
+          blocks += (jb.n_out + TPB / tpo - 1) / (TPB / tpo);
+          if (++jobs.n == 4) flush();
+        }
+      }
+      flush();
     }
   }
   if (ctr) ctr->launches += nl;

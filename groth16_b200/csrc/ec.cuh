@@ -144,6 +144,38 @@ struct alignas(16) XYZZ {
     ZZ = F::mul(ZZ, PP);
     ZZZ = F::mul(ZZZ, PPP);
   }
+  // Same mixed addition with the point's coordinates fetched on demand (x first, y only after x has been consumed):
+  // shortens the live range of the 2 x 12 (G1) / 2 x 24 (G2) limb operand in the register-bound accumulation kernel.
+  // LX(), LY() return the coordinates; the point is known not to be the identity mask-wise but may still be (0,0).
+  template <class LX, class LY>
+  G16_HD void madd_lazy(LX load_x, LY load_y, bool neg) {
+    const F px = load_x();
+    if (is_inf()) {
+      F py = load_y();
+      if (px.is_zero() && py.is_zero()) return;
+      if (neg) py = F::neg(py);
+      X = px; Y = py; ZZ = F::one(); ZZZ = F::one();
+      return;
+    }
+    const F Pd = F::sub(F::mul(px, ZZ), X);
+    F py = load_y();
+    if (px.is_zero() && py.is_zero()) return;
+    if (neg) py = F::neg(py);
+    const F R = F::sub(F::mul(py, ZZZ), Y);
+    if (Pd.is_zero()) {
+      if (R.is_zero()) *this = dbl_affine(Affine<F>{px, py});
+      else *this = inf();
+      return;
+    }
+    const F PP = F::sqr(Pd);
+    const F PPP = F::mul(Pd, PP);
+    const F Q = F::mul(X, PP);
+    const F X3 = F::sub(F::sub(F::sqr(R), PPP), F::dbl(Q));
+    Y = F::sub(F::mul(R, F::sub(Q, X3)), F::mul(Y, PPP));
+    X = X3;
+    ZZ = F::mul(ZZ, PP);
+    ZZZ = F::mul(ZZZ, PPP);
+  }
   // this += q             add-2008-s, all exceptional cases handled
   G16_HD_NOINLINE void add(const XYZZ& q) {
     if (q.is_inf()) return;

@@ -40,6 +40,13 @@ def parse():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--cpu-threads", type=int, default=0, help="threads for the CPU arm / cpu_baseline (0 = all)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--inflight", type=int, default=2, choices=[1, 2],
+                    help="proofs in flight per GPU: 2 = software pipeline over the two proof slots of a context "
+                         "(g16_prove_submit / g16_prove_wait), 1 = strictly one proof at a time")
+    ap.add_argument("--mode", default="shard", choices=["shard", "replicas"],
+                    help="N > 1: 'shard' splits every MSM of ONE proof over the GPUs (strong scaling, NCCL gather of partial "
+                         "points); 'replicas' lets every GPU prove its own proofs (weak scaling, no communication; "
+                         "BASELINE config 5)")
     return ap.parse_args()
 
 
@@ -267,9 +274,11 @@ def run_cuda(a):
     nq = g.nq
     G = GENERATORS[g.curve.name]
     t = time.time()
-    pk = g.generate_parameters_with_qap(m, *TOXIC, G["g1"], G["g2"], export=(world > 1 or not a.no_cpu_baseline))
+    pk = g.generate_parameters_with_qap(m, *TOXIC, G["g1"], G["g2"],
+                                        export=((world > 1 and a.mode == "shard") or not a.no_cpu_baseline))
+    replicas = world > 1 and a.mode == "replicas"
     sp = None
-    if world > 1:
+    if world > 1 and not replicas:
         from groth16_b200.dist import ShardedProver
         sp = ShardedProver(g, pk, None, rank, world, dev)   # keep this rank's index range of every query
     t_setup = time.time() - t
@@ -281,12 +290,45 @@ def run_cuda(a):
     proof = np.zeros(8 * nq, dtype=np.uint64)
     def step(zptr, flags):
         """one proof; returns the proof limbs (every rank computes the same proof)"""
-        if world == 1:
+        if world == 1 or replicas:
             g.prove_raw(r, s, zptr, flags, proof)
             return proof
         pf = sp.prove(r, s, zptr, flags)   # partial MSMs -> NCCL all_gather of 5 points per rank -> assemble
         proof[:2 * nq] = pf.a; proof[2 * nq:6 * nq] = pf.b; proof[6 * nq:] = pf.c
         return proof
+
+    def run_steps(zptr, flags, steps):
+        """`steps` complete proofs; with --inflight 2 proof i+1 is submitted before proof i is waited for"""
+        dev_ms, launches = [], 0
+        if a.inflight == 1:
+            for _ in range(steps):
+                step(zptr, flags)
+                tm = g.timings()
+                dev_ms.append(tm["total_ms"]); launches += tm["launches"]
+            return dev_ms, launches
+
+        def submit(slot):
+            if world == 1 or replicas:
+                g.prove_submit_raw(slot, r, s, zptr, flags)
+            else:
+                sp.submit(slot, r, zptr, flags)
+
+        def finish(slot):
+            if world == 1 or replicas:
+                g.prove_wait_raw(slot, proof)
+            else:
+                pf = sp.finish(slot, r, s)
+                proof[:2 * nq] = pf.a; proof[2 * nq:6 * nq] = pf.b; proof[6 * nq:] = pf.c
+            tm = g.timings()
+            dev_ms.append(tm["total_ms"])
+            return tm["launches"]
+
+        submit(0)
+        for i in range(1, steps):
+            submit(i & 1)
+            launches += finish((i - 1) & 1)
+        launches += finish((steps - 1) & 1)
+        return dev_ms, launches
 
     def timed(zptr, flags, steps, sampler=None):
         if world > 1:
@@ -295,13 +337,7 @@ def run_cuda(a):
         if sampler:
             sampler.start()
         t0 = time.perf_counter()
-        dev_ms = []
-        launches = 0
-        for _ in range(steps):
-            step(zptr, flags)
-            tm = g.timings()
-            dev_ms.append(tm["total_ms"])
-            launches += tm["launches"]
+        dev_ms, launches = run_steps(zptr, flags, steps)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -313,13 +349,24 @@ def run_cuda(a):
             dt = float(tt.item())
         return dt, dev_ms, launches, clocks
 
+    def single_latency(zptr, flags, reps=5):
+        """one proof at a time (no pipelining): wall-clock latency per proof"""
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            step(zptr, flags)
+        torch.cuda.synchronize()
+        return 1e3 * (time.perf_counter() - t0) / reps
+
     # ---- warm-up, then the resident-input measurement (`value`) ----
     for _ in range(max(a.warmup, 3)):
         step(z_dev.data_ptr(), _lib.ASSIGNMENT_ON_DEVICE)
     first = step(z_dev.data_ptr(), _lib.ASSIGNMENT_ON_DEVICE).copy()
     sampler = ClockSampler(local) if rank == 0 else None
     dt, dev_ms, launches, clocks = timed(z_dev.data_ptr(), _lib.ASSIGNMENT_ON_DEVICE, a.steps, sampler)
-    value = a.steps / dt
+    units = world if replicas else 1          # proofs completed per step across the job
+    value = units * a.steps / dt
+    lat_ms = single_latency(z_dev.data_ptr(), _lib.ASSIGNMENT_ON_DEVICE)
     # ---- end to end through the public call with HOST buffers: pinned assignment in, proof out ----
     for _ in range(2):
         step(z_pinned.data_ptr(), 0)
@@ -377,16 +424,22 @@ def run_cuda(a):
                              f"{tms[1]:.0f} ms), restated ark CPU path; proof bit-identical to the CUDA proof"}
         line = {
             "metric": METRIC, "value": value, "unit": "proofs/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
-            "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak" if replicas else "strong",
+            "vs_baseline": None,
             "dtype": "u32 limbs (255-bit Fr / 381-bit Fq Montgomery integers)", "data": "synthetic",
             "config": {"workload": workload_name(a), "curve": a.curve, "log_n": a.log_n,
-                       "parallelism": f"msm-shard{world}" if world > 1 else "single-gpu",
+                       "parallelism": (f"replicas{world} (one independent proof per GPU per step)" if replicas else
+                                       f"msm-shard{world} (one proof per step, MSM pairs split by index range)") if world > 1 else "single-gpu",
+                       "inflight": a.inflight,
                        "l2": "inputs exceed L2: resident proving key with precomputed multiples (GBs) + 32 MiB assignment + "
                              "sorted digit arrays (134 MB per MSM) are streamed every step",
-                       "timing": "wall clock around K synchronous proofs bracketed by barrier+synchronize (host Horner/assembly "
-                                 "included), max over ranks; device_ms_per_step = CUDA-event span of the GPU work"},
+                       "timing": "wall clock around K complete proofs bracketed by barrier+synchronize (host finish/assembly "
+                                 "included), max over ranks; with inflight=2 proof i+1 is submitted before proof i is waited "
+                                 "for (two proof slots per context); device_ms_per_step = CUDA-event span of one proof's GPU "
+                                 "work; latency_ms_single_proof = one proof at a time"},
             "device_ms_per_step": statistics.mean(dev_ms),
-            "e2e": {"value": a.steps / dt_e2e, "unit": "proofs/s", "h2d_bytes_per_step": int(tm_e2e["h2d_bytes"]),
+            "latency_ms_single_proof": lat_ms,
+            "e2e": {"value": units * a.steps / dt_e2e, "unit": "proofs/s", "h2d_bytes_per_step": int(tm_e2e["h2d_bytes"]),
                     "d2h_bytes_per_step": int(tm_e2e["d2h_bytes"]), "ms_per_step": 1e3 * dt_e2e / a.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,

@@ -306,6 +306,20 @@ class Groth16:
         """Thin call used by bench.py: everything already in ABI form; z_ptr is a host or device address."""
         _check(self._lib.g16_prove(self._ctx, _ptr(r_limbs), _ptr(s_limbs), C.c_void_p(z_ptr), flags, _ptr(out)))
 
+    # ---- pipelined proving: two slots per context (g16_prove_submit / g16_prove_wait) ----
+    def prove_submit_raw(self, slot: int, r_limbs: np.ndarray, s_limbs: np.ndarray, z_ptr, flags: int):
+        """Enqueue a whole proof on `slot` and return; r/s/z buffers must stay alive until prove_wait_raw(slot)."""
+        _check(self._lib.g16_prove_submit(self._ctx, slot, _ptr(r_limbs), _ptr(s_limbs), C.c_void_p(z_ptr), flags))
+
+    def prove_wait_raw(self, slot: int, out: np.ndarray):
+        _check(self._lib.g16_prove_wait(self._ctx, slot, _ptr(out)))
+
+    def prove_partial_submit_raw(self, slot: int, r_limbs: np.ndarray, z_ptr, flags: int):
+        _check(self._lib.g16_prove_partial_submit(self._ctx, slot, _ptr(r_limbs), C.c_void_p(z_ptr), flags))
+
+    def prove_partial_wait_raw(self, slot: int, out: np.ndarray):
+        _check(self._lib.g16_prove_partial_wait(self._ctx, slot, _ptr(out)))
+
     def prove_partial_raw(self, r_limbs: np.ndarray, z_ptr, flags: int, out: np.ndarray):
         _check(self._lib.g16_prove_partial(self._ctx, _ptr(r_limbs), C.c_void_p(z_ptr), flags, _ptr(out)))
 

@@ -100,6 +100,22 @@ int g16_prove_assemble(g16_ctx* ctx, const uint64_t* r, const uint64_t* s, const
   CTX_OR_FAIL(ctx);
   return ctx->eng->prove_assemble(r, s, partials, nparts, proof_out);
 }
+int g16_prove_submit(g16_ctx* ctx, int slot, const uint64_t* r, const uint64_t* s, const uint64_t* full_assignment, uint32_t flags) {
+  CTX_OR_FAIL(ctx);
+  return ctx->eng->prove_submit(slot, r, s, full_assignment, flags);
+}
+int g16_prove_wait(g16_ctx* ctx, int slot, uint64_t* proof_out) {
+  CTX_OR_FAIL(ctx);
+  return ctx->eng->prove_wait(slot, proof_out);
+}
+int g16_prove_partial_submit(g16_ctx* ctx, int slot, const uint64_t* r, const uint64_t* full_assignment, uint32_t flags) {
+  CTX_OR_FAIL(ctx);
+  return ctx->eng->partial_submit(slot, r, full_assignment, flags);
+}
+int g16_prove_partial_wait(g16_ctx* ctx, int slot, uint64_t* partial_out) {
+  CTX_OR_FAIL(ctx);
+  return ctx->eng->partial_wait(slot, partial_out);
+}
 int g16_witness_map(g16_ctx* ctx, const uint64_t* full_assignment, uint32_t flags, uint64_t* h_out) {
   CTX_OR_FAIL(ctx);
   return ctx->eng->witness_map(full_assignment, flags, h_out);

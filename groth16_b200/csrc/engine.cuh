@@ -48,6 +48,10 @@ struct IEngine {
   virtual int prove(const uint64_t* r, const uint64_t* s, const uint64_t* z, uint32_t flags, uint64_t* proof) = 0;
   virtual int prove_partial(const uint64_t* r, const uint64_t* z, uint32_t flags, uint64_t* partial) = 0;
   virtual int prove_assemble(const uint64_t* r, const uint64_t* s, const uint64_t* partials, uint32_t nparts, uint64_t* proof) = 0;
+  virtual int prove_submit(int slot, const uint64_t* r, const uint64_t* s, const uint64_t* z, uint32_t flags) = 0;
+  virtual int prove_wait(int slot, uint64_t* proof) = 0;
+  virtual int partial_submit(int slot, const uint64_t* r, const uint64_t* z, uint32_t flags) = 0;
+  virtual int partial_wait(int slot, uint64_t* partial) = 0;
   virtual int witness_map(const uint64_t* z, uint32_t flags, uint64_t* h) = 0;
   virtual uint32_t domain_log() const = 0;
   g16_timings tm{};
@@ -68,12 +72,30 @@ struct Engine : IEngine {
   enum { M_H = 0, M_L = 1, M_A = 2, M_B1 = 3, M_B2 = 4 };
 
   int device = 0;
-  cudaStream_t st_main = nullptr, st_msm[5] = {};
-  cudaEvent_t ev_start = nullptr, ev_z = nullptr, ev_h = nullptr, ev_m0[5] = {}, ev_m1[5] = {}, ev_a0[5] = {}, ev_a1[5] = {};
+  // Everything one in-flight proof owns: streams, events, work vectors, MSM workspaces, timings.  Two slots allow a
+  // software pipeline (g16_prove_submit / g16_prove_wait): the latency-bound tail of proof i overlaps the bulk of proof i+1.
+  struct FixedMuls { P1 r_d1, s_d1, rs_d1; P2 s_d2; };
+  struct Partials { P1 h, l, a, b1; P2 b2; };
+  struct Slot {
+    cudaStream_t st_main = nullptr, st_msm[5] = {};
+    cudaEvent_t ev_start = nullptr, ev_z = nullptr, ev_h = nullptr, ev_m0[5] = {}, ev_m1[5] = {}, ev_a0[5] = {}, ev_a1[5] = {};
+    DevBuf d_z, d_a, d_b, d_c, d_t, d_h;
+    MsmWorkspace<Fq> ws1[4];
+    MsmWorkspace<Fq2> ws2;
+    g16_timings tm{};
+    // state of the submission in flight
+    bool busy = false, serial = false, have_s = false;
+    bool run[5] = {};
+    MsmGeom geom[5] = {};
+    Fr r, s;
+    FixedMuls fx;
+    std::thread helper;
+    unsigned long long launches0 = 0;
+  };
+  static constexpr int NSLOTS = 2;
+  Slot slots[NSLOTS];
+  Slot& S0 = slots[0];   // slot used by the synchronous entry points
   NttDomain<Fr> dom;
-  DevBuf d_z, d_a, d_b, d_c, d_t, d_h;
-  MsmWorkspace<Fq> ws1[4];
-  MsmWorkspace<Fq2> ws2;
   MsmCounters ctr;
   unsigned long long ntt_launches = 0;
 
@@ -118,7 +140,7 @@ struct Engine : IEngine {
   int finish_query(Query& x) {   // x.bases holds copy 0; build the other copies and the infinity mask
     const uint64_t cnt = x.hi - x.lo;
     G16_CUDA(x.mask.reserve(cnt + 16));
-    G16_CUDA(msm_prepare_query<F>(st_main, x.bases.template as<Affine<F>>(), (uint32_t)cnt, x.geom.copies, x.geom.c * x.geom.ne,
+    G16_CUDA(msm_prepare_query<F>(S0.st_main, x.bases.template as<Affine<F>>(), (uint32_t)cnt, x.geom.copies, x.geom.c * x.geom.ne,
                                   x.mask.template as<uint8_t>()));
     return G16_OK;
   }
@@ -148,36 +170,43 @@ struct Engine : IEngine {
     int prio_lo = 0, prio_hi = 0;
     G16_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));   // lo = least priority (numerically greatest)
     auto level = [&](int k) { return std::min(prio_lo, prio_hi + k); };
-    G16_CUDA(cudaStreamCreateWithPriority(&st_main, cudaStreamNonBlocking, level(0)));
-    for (int i = 0; i < 5; i++) {
-      const int pr = i == M_B2 ? level(1) : (i == M_H ? level(2) : prio_lo);
-      G16_CUDA(cudaStreamCreateWithPriority(&st_msm[i], cudaStreamNonBlocking, pr));
-    }
-    G16_CUDA(cudaEventCreate(&ev_start));
-    G16_CUDA(cudaEventCreate(&ev_z));
-    G16_CUDA(cudaEventCreate(&ev_h));
-    for (int i = 0; i < 5; i++) {
-      G16_CUDA(cudaEventCreate(&ev_m0[i]));
-      G16_CUDA(cudaEventCreate(&ev_m1[i]));
-      G16_CUDA(cudaEventCreate(&ev_a0[i]));
-      G16_CUDA(cudaEventCreate(&ev_a1[i]));
+    for (Slot& sl : slots) {
+      G16_CUDA(cudaStreamCreateWithPriority(&sl.st_main, cudaStreamNonBlocking, level(0)));
+      for (int i = 0; i < 5; i++) {
+        const int pr = i == M_B2 ? level(1) : (i == M_H ? level(2) : prio_lo);
+        G16_CUDA(cudaStreamCreateWithPriority(&sl.st_msm[i], cudaStreamNonBlocking, pr));
+      }
+      G16_CUDA(cudaEventCreate(&sl.ev_start));
+      G16_CUDA(cudaEventCreate(&sl.ev_z));
+      G16_CUDA(cudaEventCreate(&sl.ev_h));
+      for (int i = 0; i < 5; i++) {
+        G16_CUDA(cudaEventCreate(&sl.ev_m0[i]));
+        G16_CUDA(cudaEventCreate(&sl.ev_m1[i]));
+        G16_CUDA(cudaEventCreate(&sl.ev_a0[i]));
+        G16_CUDA(cudaEventCreate(&sl.ev_a1[i]));
+      }
     }
     return G16_OK;
   }
   ~Engine() override {
     cudaSetDevice(device);
+    for (Slot& sl : slots)
+      if (sl.helper.joinable()) sl.helper.join();
     cudaDeviceSynchronize();
     dom.release();
-    d_z.release(); d_a.release(); d_b.release(); d_c.release(); d_t.release(); d_h.release();
-    for (auto& w : ws1) w.release();
-    ws2.release();
+    for (Slot& sl : slots) {
+      sl.d_z.release(); sl.d_a.release(); sl.d_b.release(); sl.d_c.release(); sl.d_t.release(); sl.d_h.release();
+      for (auto& w : sl.ws1) w.release();
+      sl.ws2.release();
+      if (sl.st_main) cudaStreamDestroy(sl.st_main);
+      for (auto s : sl.st_msm) if (s) cudaStreamDestroy(s);
+      auto kill = [](cudaEvent_t ev) { if (ev) cudaEventDestroy(ev); };
+      kill(sl.ev_start); kill(sl.ev_z); kill(sl.ev_h);
+      for (int i = 0; i < 5; i++) { kill(sl.ev_m0[i]); kill(sl.ev_m1[i]); kill(sl.ev_a0[i]); kill(sl.ev_a1[i]); }
+    }
     for (int m = 0; m < 3; m++) { csr_rp[m].release(); csr_col[m].release(); csr_val[m].release(); }
     for (auto& x : q) { x.bases.release(); x.mask.release(); }
     d_gamma_abc.release(); full_a.release(); full_b1.release(); full_b2.release();
-    if (st_main) cudaStreamDestroy(st_main);
-    for (auto s : st_msm) if (s) cudaStreamDestroy(s);
-    for (cudaEvent_t e : {ev_start, ev_z, ev_h}) if (e) cudaEventDestroy(e);
-    for (int i = 0; i < 5; i++) for (cudaEvent_t e : {ev_m0[i], ev_m1[i], ev_a0[i], ev_a1[i]}) if (e) cudaEventDestroy(e);
   }
   int fq_limbs() const override { return NQ64; }
   int partial_limbs() const override { return 4 * 2 * NQ64 + 4 * NQ64; }
@@ -217,15 +246,19 @@ struct Engine : IEngine {
   }
 
   // ---- domain + buffers ----
+  int ensure_slot_buffers(Slot& sl, int Ln) {
+    const size_t bytes = (size_t)sizeof(Fr) << Ln;
+    G16_CUDA(sl.d_a.reserve(bytes)); G16_CUDA(sl.d_b.reserve(bytes)); G16_CUDA(sl.d_c.reserve(bytes));
+    G16_CUDA(sl.d_t.reserve(bytes)); G16_CUDA(sl.d_h.reserve(bytes));
+    return G16_OK;
+  }
   int ensure_domain(int Ln) {
     if (dom.L != Ln) {
-      G16_CUDA(cudaStreamSynchronize(st_main));
-      G16_CUDA(ntt_domain_build(dom, Ln, st_main, &ntt_launches));
+      G16_CUDA(cudaDeviceSynchronize());
+      G16_CUDA(ntt_domain_build(dom, Ln, S0.st_main, &ntt_launches));
+      G16_CUDA(cudaStreamSynchronize(S0.st_main));
     }
-    const size_t bytes = (size_t)sizeof(Fr) << Ln;
-    G16_CUDA(d_a.reserve(bytes)); G16_CUDA(d_b.reserve(bytes)); G16_CUDA(d_c.reserve(bytes));
-    G16_CUDA(d_t.reserve(bytes)); G16_CUDA(d_h.reserve(bytes));
-    return G16_OK;
+    return ensure_slot_buffers(S0, Ln);
   }
 
   // ---- NTT API ----
@@ -236,34 +269,35 @@ struct Engine : IEngine {
     G16_CUDA(cudaSetDevice(device));
     if ((rc = ensure_domain((int)log_n))) return rc;
     const size_t bytes = (size_t)sizeof(Fr) << log_n;
-    Fr* x = d_a.template as<Fr>();
-    Fr* y = d_t.template as<Fr>();
-    G16_CUDA(cudaMemcpyAsync(x, inout, bytes, cudaMemcpyHostToDevice, st_main));
+    Fr* x = S0.d_a.template as<Fr>();
+    Fr* y = S0.d_t.template as<Fr>();
+    G16_CUDA(cudaMemcpyAsync(x, inout, bytes, cudaMemcpyHostToDevice, S0.st_main));
     const Fr zero = Fr::zero();
     if (!inverse)
-      ntt_run<Fr>(st_main, dom, false, x, x, y, coset ? NTT_LOAD_MUL_TABLE : NTT_LOAD_PLAIN, dom.coset_fwd, nullptr, nullptr, zero,
+      ntt_run<Fr>(S0.st_main, dom, false, x, x, y, coset ? NTT_LOAD_MUL_TABLE : NTT_LOAD_PLAIN, dom.coset_fwd, nullptr, nullptr, zero,
                   NTT_STORE_PLAIN, nullptr, zero, &ntt_launches);
     else
-      ntt_run<Fr>(st_main, dom, true, x, x, y, NTT_LOAD_PLAIN, nullptr, nullptr, nullptr, zero,
+      ntt_run<Fr>(S0.st_main, dom, true, x, x, y, NTT_LOAD_PLAIN, nullptr, nullptr, nullptr, zero,
                   coset ? NTT_STORE_MUL_TABLE : NTT_STORE_MUL_CONST, dom.coset_inv, dom.n_inv, &ntt_launches);
     G16_CUDA(cudaGetLastError());
-    G16_CUDA(cudaMemcpyAsync(inout, y, bytes, cudaMemcpyDeviceToHost, st_main));
-    G16_CUDA(cudaStreamSynchronize(st_main));
+    G16_CUDA(cudaMemcpyAsync(inout, y, bytes, cudaMemcpyDeviceToHost, S0.st_main));
+    G16_CUDA(cudaStreamSynchronize(S0.st_main));
     return G16_OK;
   }
 
-  // a, b, c (device, evaluations over the domain) -> d_h (coefficients of h).  r1cs_to_qap.rs:201-232
-  void witness_map_device() {
-    Fr* A = d_a.template as<Fr>(); Fr* B = d_b.template as<Fr>(); Fr* C = d_c.template as<Fr>(); Fr* T = d_t.template as<Fr>(); Fr* H = d_h.template as<Fr>();
+  // a, b, c (device, evaluations over the domain) -> S0.d_h (coefficients of h).  r1cs_to_qap.rs:201-232
+  void witness_map_device(Slot& sl) {
+    cudaStream_t st = sl.st_main;
+    Fr* A = sl.d_a.template as<Fr>(); Fr* B = sl.d_b.template as<Fr>(); Fr* C = sl.d_c.template as<Fr>(); Fr* T = sl.d_t.template as<Fr>(); Fr* H = sl.d_h.template as<Fr>();
     const Fr zero = Fr::zero();
     for (Fr* X : {A, B, C}) {
       // domain.ifft_in_place (r1cs_to_qap.rs:201-202,220)
-      ntt_run<Fr>(st_main, dom, true, X, X, T, NTT_LOAD_PLAIN, nullptr, nullptr, nullptr, zero, NTT_STORE_MUL_CONST, nullptr, dom.n_inv, &ntt_launches);
+      ntt_run<Fr>(st, dom, true, X, X, T, NTT_LOAD_PLAIN, nullptr, nullptr, nullptr, zero, NTT_STORE_MUL_CONST, nullptr, dom.n_inv, &ntt_launches);
       // coset_domain.fft_in_place (r1cs_to_qap.rs:204-207,221)
-      ntt_run<Fr>(st_main, dom, false, T, T, X, NTT_LOAD_MUL_TABLE, dom.coset_fwd, nullptr, nullptr, zero, NTT_STORE_PLAIN, nullptr, zero, &ntt_launches);
+      ntt_run<Fr>(st, dom, false, T, T, X, NTT_LOAD_MUL_TABLE, dom.coset_fwd, nullptr, nullptr, zero, NTT_STORE_PLAIN, nullptr, zero, &ntt_launches);
     }
     // (a*b - c) * Z^-1 fused into the load of coset_domain.ifft_in_place (r1cs_to_qap.rs:209,223-232)
-    ntt_run<Fr>(st_main, dom, true, A, T, H, NTT_LOAD_AB_MINUS_C, nullptr, B, C, dom.z_inv, NTT_STORE_MUL_TABLE, dom.coset_inv, zero, &ntt_launches);
+    ntt_run<Fr>(st, dom, true, A, T, H, NTT_LOAD_AB_MINUS_C, nullptr, B, C, dom.z_inv, NTT_STORE_MUL_TABLE, dom.coset_inv, zero, &ntt_launches);
   }
 
   int witness_map_evals(uint32_t log_n, const uint64_t* a, const uint64_t* b, const uint64_t* c, uint64_t* h) override {
@@ -273,13 +307,13 @@ struct Engine : IEngine {
     G16_CUDA(cudaSetDevice(device));
     if ((rc = ensure_domain((int)log_n))) return rc;
     const size_t bytes = (size_t)sizeof(Fr) << log_n;
-    G16_CUDA(cudaMemcpyAsync(d_a.p, a, bytes, cudaMemcpyHostToDevice, st_main));
-    G16_CUDA(cudaMemcpyAsync(d_b.p, b, bytes, cudaMemcpyHostToDevice, st_main));
-    G16_CUDA(cudaMemcpyAsync(d_c.p, c, bytes, cudaMemcpyHostToDevice, st_main));
-    witness_map_device();
+    G16_CUDA(cudaMemcpyAsync(S0.d_a.p, a, bytes, cudaMemcpyHostToDevice, S0.st_main));
+    G16_CUDA(cudaMemcpyAsync(S0.d_b.p, b, bytes, cudaMemcpyHostToDevice, S0.st_main));
+    G16_CUDA(cudaMemcpyAsync(S0.d_c.p, c, bytes, cudaMemcpyHostToDevice, S0.st_main));
+    witness_map_device(S0);
     G16_CUDA(cudaGetLastError());
-    G16_CUDA(cudaMemcpyAsync(h, d_h.p, bytes, cudaMemcpyDeviceToHost, st_main));
-    G16_CUDA(cudaStreamSynchronize(st_main));
+    G16_CUDA(cudaMemcpyAsync(h, S0.d_h.p, bytes, cudaMemcpyDeviceToHost, S0.st_main));
+    G16_CUDA(cudaStreamSynchronize(S0.st_main));
     return G16_OK;
   }
 
@@ -295,13 +329,13 @@ struct Engine : IEngine {
       G16_CUDA(db.reserve(n * sizeof(Affine<F>)));
       G16_CUDA(ds.reserve(n * 32));
       G16_CUDA(dm.reserve(n));
-      G16_CUDA(cudaMemcpyAsync(db.p, bases, n * sizeof(Affine<F>), cudaMemcpyHostToDevice, st_main));
-      G16_CUDA(cudaMemcpyAsync(ds.p, scalars, n * 32, cudaMemcpyHostToDevice, st_main));
-      G16_CUDA(msm_prepare_query<F>(st_main, db.template as<Affine<F>>(), (uint32_t)n, 1, 0, dm.template as<uint8_t>()));
+      G16_CUDA(cudaMemcpyAsync(db.p, bases, n * sizeof(Affine<F>), cudaMemcpyHostToDevice, S0.st_main));
+      G16_CUDA(cudaMemcpyAsync(ds.p, scalars, n * 32, cudaMemcpyHostToDevice, S0.st_main));
+      G16_CUDA(msm_prepare_query<F>(S0.st_main, db.template as<Affine<F>>(), (uint32_t)n, 1, 0, dm.template as<uint8_t>()));
       const MsmGeom g = with_k0(msm_geom(n, FR_BITS, cfg_c, 0), sizeof(F) > 48);   // caller-supplied bases: no precomputed copies
-      cudaError_t e = msm_enqueue<F, Fr>(st_main, ws, g, db.template as<Affine<F>>(), dm.template as<uint8_t>(), ds.template as<uint32_t>(), false, &ctr, nullptr, nullptr);
+      cudaError_t e = msm_enqueue<F, Fr>(S0.st_main, ws, g, db.template as<Affine<F>>(), dm.template as<uint8_t>(), ds.template as<uint32_t>(), false, &ctr, nullptr, nullptr);
       if (e != cudaSuccess) { db.release(); ds.release(); dm.release(); return fail(G16_ERR_CUDA, std::string("msm_enqueue: ") + cudaGetErrorString(e)); }
-      e = cudaStreamSynchronize(st_main);
+      e = cudaStreamSynchronize(S0.st_main);
       db.release(); ds.release(); dm.release();
       if (e != cudaSuccess) return fail(G16_ERR_CUDA, std::string("msm sync: ") + cudaGetErrorString(e));
       res = msm_finish<F>(ws, g);
@@ -309,8 +343,8 @@ struct Engine : IEngine {
     store_proj<F>(out, res);
     return G16_OK;
   }
-  int msm_g1(const uint64_t* bases, const uint64_t* scalars, uint64_t n, uint64_t* out) override { return msm_host<Fq>(ws1[0], bases, scalars, n, out); }
-  int msm_g2(const uint64_t* bases, const uint64_t* scalars, uint64_t n, uint64_t* out) override { return msm_host<Fq2>(ws2, bases, scalars, n, out); }
+  int msm_g1(const uint64_t* bases, const uint64_t* scalars, uint64_t n, uint64_t* out) override { return msm_host<Fq>(S0.ws1[0], bases, scalars, n, out); }
+  int msm_g2(const uint64_t* bases, const uint64_t* scalars, uint64_t n, uint64_t* out) override { return msm_host<Fq2>(S0.ws2, bases, scalars, n, out); }
 
   // ---- circuit ----
   int circuit_load(uint32_t ni, uint32_t nc, uint32_t nw, const g16_csr* a, const g16_csr* b, const g16_csr* c) override {
@@ -342,9 +376,9 @@ struct Engine : IEngine {
       }
     }
     num_inputs = ni; num_constraints = nc; num_witness = nw; L = Ln;
-    G16_CUDA(d_z.reserve((size_t)nvars * 32));
+    G16_CUDA(S0.d_z.reserve((size_t)nvars * 32));
     if ((rc = ensure_domain(L))) return rc;
-    G16_CUDA(cudaStreamSynchronize(st_main));
+    G16_CUDA(cudaStreamSynchronize(S0.st_main));
     have_circuit = true;
     have_pk = false;
     return G16_OK;
@@ -364,7 +398,7 @@ struct Engine : IEngine {
     G16_CUDA(x.bases.reserve((size_t)x.geom.copies * cnt * sizeof(AT) + 16));
     if (cnt) {
       const size_t limbs = sizeof(AT) / 8;
-      G16_CUDA(cudaMemcpyAsync(x.bases.p, host_full + (skip_first + x.lo) * limbs, cnt * sizeof(AT), cudaMemcpyHostToDevice, st_main));
+      G16_CUDA(cudaMemcpyAsync(x.bases.p, host_full + (skip_first + x.lo) * limbs, cnt * sizeof(AT), cudaMemcpyHostToDevice, S0.st_main));
     }
     return finish_query<F>(x);
   }
@@ -395,7 +429,7 @@ struct Engine : IEngine {
     a0 = load_a1(pk->a_query); b1_0 = load_a1(pk->b_g1_query); b2_0 = load_a2(pk->b_g2_query);
     alpha_g1 = load_a1(pk->alpha_g1); beta_g1 = load_a1(pk->beta_g1); delta_g1 = load_a1(pk->delta_g1);
     beta_g2 = load_a2(pk->beta_g2); delta_g2 = load_a2(pk->delta_g2);
-    G16_CUDA(cudaStreamSynchronize(st_main));
+    G16_CUDA(cudaStreamSynchronize(S0.st_main));
     have_pk = true;
     from_setup = false;
     return G16_OK;
@@ -405,7 +439,7 @@ struct Engine : IEngine {
   template <class F>
   int batch_mul(const Affine<F>& gen, const Fr* d_scalars, uint64_t cnt, Affine<F>* d_out, DevBuf& table) {
     G16_CUDA(table.reserve((size_t)FB_WINDOWS * 255 * sizeof(XYZZ<F>)));
-    G16_CUDA((fb_batch_mul<F, Fr>(st_main, gen, d_scalars, cnt, d_out, table.template as<XYZZ<F>>())));
+    G16_CUDA((fb_batch_mul<F, Fr>(S0.st_main, gen, d_scalars, cnt, d_out, table.template as<XYZZ<F>>())));
     return G16_OK;
   }
   int setup(const uint64_t* alpha_, const uint64_t* beta_, const uint64_t* gamma_, const uint64_t* delta_,
@@ -467,7 +501,7 @@ struct Engine : IEngine {
     G16_CUDA(d_s.reserve(maxs * 32));
     int rc;
     auto up = [&](const std::vector<Fr>& v) -> cudaError_t {
-      return v.empty() ? cudaSuccess : cudaMemcpyAsync(d_s.p, v.data(), v.size() * 32, cudaMemcpyHostToDevice, st_main);
+      return v.empty() ? cudaSuccess : cudaMemcpyAsync(d_s.p, v.data(), v.size() * 32, cudaMemcpyHostToDevice, S0.st_main);
     };
     G16_CUDA(full_a.reserve(nv * sizeof(A1))); G16_CUDA(full_b1.reserve(nv * sizeof(A1))); G16_CUDA(full_b2.reserve(nv * sizeof(A2)));
     G16_CUDA(d_gamma_abc.reserve((size_t)ni * sizeof(A1)));
@@ -476,20 +510,20 @@ struct Engine : IEngine {
     G16_CUDA(q[M_L].bases.reserve((size_t)q[M_L].geom.copies * num_witness * sizeof(A1) + 16));
     // a_query / b_g1_query / b_g2_query
     G16_CUDA(up(qa)); if ((rc = batch_mul<Fq>(g1, d_s.template as<Fr>(), nv, full_a.template as<A1>(), tab1))) return rc;
-    G16_CUDA(cudaStreamSynchronize(st_main));
+    G16_CUDA(cudaStreamSynchronize(S0.st_main));
     G16_CUDA(up(qb)); if ((rc = batch_mul<Fq>(g1, d_s.template as<Fr>(), nv, full_b1.template as<A1>(), tab1))) return rc;
     if ((rc = batch_mul<Fq2>(g2, d_s.template as<Fr>(), nv, full_b2.template as<A2>(), tab2))) return rc;
-    G16_CUDA(cudaStreamSynchronize(st_main));
+    G16_CUDA(cudaStreamSynchronize(S0.st_main));
     G16_CUDA(up(hs)); if ((rc = batch_mul<Fq>(g1, d_s.template as<Fr>(), n - 1, q[M_H].bases.template as<A1>(), tab1))) return rc;
-    G16_CUDA(cudaStreamSynchronize(st_main));
+    G16_CUDA(cudaStreamSynchronize(S0.st_main));
     G16_CUDA(up(lq)); if ((rc = batch_mul<Fq>(g1, d_s.template as<Fr>(), num_witness, q[M_L].bases.template as<A1>(), tab1))) return rc;
-    G16_CUDA(cudaStreamSynchronize(st_main));
+    G16_CUDA(cudaStreamSynchronize(S0.st_main));
     G16_CUDA(up(gabc)); if ((rc = batch_mul<Fq>(g1, d_s.template as<Fr>(), ni, d_gamma_abc.template as<A1>(), tab1))) return rc;
-    G16_CUDA(cudaStreamSynchronize(st_main));
+    G16_CUDA(cudaStreamSynchronize(S0.st_main));
     // MSM views: query[1..]
     auto view = [&](Query& x, DevBuf& full, size_t esz) -> int {
       G16_CUDA(x.bases.reserve((size_t)x.geom.copies * (nv - 1) * esz + 16));
-      if (nv > 1) G16_CUDA(cudaMemcpyAsync(x.bases.p, (char*)full.p + esz, (nv - 1) * esz, cudaMemcpyDeviceToDevice, st_main));
+      if (nv > 1) G16_CUDA(cudaMemcpyAsync(x.bases.p, (char*)full.p + esz, (nv - 1) * esz, cudaMemcpyDeviceToDevice, S0.st_main));
       return G16_OK;
     };
     if ((rc = view(q[M_A], full_a, sizeof(A1)))) return rc;
@@ -498,10 +532,10 @@ struct Engine : IEngine {
     for (int m = 0; m < 5; m++) {
       if ((rc = (m == M_B2) ? finish_query<Fq2>(q[m]) : finish_query<Fq>(q[m]))) return rc;
     }
-    G16_CUDA(cudaMemcpyAsync(&a0, full_a.p, sizeof(A1), cudaMemcpyDeviceToHost, st_main));
-    G16_CUDA(cudaMemcpyAsync(&b1_0, full_b1.p, sizeof(A1), cudaMemcpyDeviceToHost, st_main));
-    G16_CUDA(cudaMemcpyAsync(&b2_0, full_b2.p, sizeof(A2), cudaMemcpyDeviceToHost, st_main));
-    G16_CUDA(cudaStreamSynchronize(st_main));
+    G16_CUDA(cudaMemcpyAsync(&a0, full_a.p, sizeof(A1), cudaMemcpyDeviceToHost, S0.st_main));
+    G16_CUDA(cudaMemcpyAsync(&b1_0, full_b1.p, sizeof(A1), cudaMemcpyDeviceToHost, S0.st_main));
+    G16_CUDA(cudaMemcpyAsync(&b2_0, full_b2.p, sizeof(A2), cudaMemcpyDeviceToHost, S0.st_main));
+    G16_CUDA(cudaStreamSynchronize(S0.st_main));
     // single points on the host (generator.rs:147-151,182)
     uint32_t k[8];
     auto mul1 = [&](const Fr& s) { fr_to_canon(s, k); return P1::from_affine(g1).mul_u32(k, 8).to_affine(); };
@@ -534,117 +568,136 @@ struct Engine : IEngine {
   }
 
   // ---- proving ----
-  // enqueue: upload z, row evaluation, witness map on st_main
-  int enqueue_witness_map(const uint64_t* z, uint32_t flags) {
+  // enqueue on sl.st_main: upload z, row evaluation, witness map
+  int enqueue_witness_map(Slot& sl, const uint64_t* z, uint32_t flags) {
     const uint64_t nv = nvars();
-    tm.h2d_bytes = 0;
-    G16_CUDA(cudaEventRecord(ev_start, st_main));
+    int rc = ensure_slot_buffers(sl, L);
+    if (rc) return rc;
+    G16_CUDA(sl.d_z.reserve((size_t)nv * 32));
+    sl.tm.h2d_bytes = 0;
+    G16_CUDA(cudaEventRecord(sl.ev_start, sl.st_main));
     if (flags & G16_ASSIGNMENT_ON_DEVICE) {
-      G16_CUDA(cudaMemcpyAsync(d_z.p, z, nv * 32, cudaMemcpyDeviceToDevice, st_main));
+      G16_CUDA(cudaMemcpyAsync(sl.d_z.p, z, nv * 32, cudaMemcpyDeviceToDevice, sl.st_main));
     } else {
-      G16_CUDA(cudaMemcpyAsync(d_z.p, z, nv * 32, cudaMemcpyHostToDevice, st_main));
-      tm.h2d_bytes = nv * 32;
+      G16_CUDA(cudaMemcpyAsync(sl.d_z.p, z, nv * 32, cudaMemcpyHostToDevice, sl.st_main));
+      sl.tm.h2d_bytes = nv * 32;
     }
-    G16_CUDA(cudaEventRecord(ev_z, st_main));
+    G16_CUDA(cudaEventRecord(sl.ev_z, sl.st_main));
     const uint32_t n = 1u << L;
     CsrDev cs[3];
     for (int m = 0; m < 3; m++) cs[m] = CsrDev{csr_rp[m].template as<uint32_t>(), csr_col[m].template as<uint32_t>(), csr_val[m].p};
-    r1cs_matvec<Fr>(st_main, cs, d_z.template as<Fr>(), num_constraints, num_inputs, n, d_a.template as<Fr>(), d_b.template as<Fr>(),
-                    d_c.template as<Fr>());
+    r1cs_matvec<Fr>(sl.st_main, cs, sl.d_z.template as<Fr>(), num_constraints, num_inputs, n, sl.d_a.template as<Fr>(),
+                    sl.d_b.template as<Fr>(), sl.d_c.template as<Fr>());
     ntt_launches++;
-    witness_map_device();
+    witness_map_device(sl);
     G16_CUDA(cudaGetLastError());
-    G16_CUDA(cudaEventRecord(ev_h, st_main));
+    G16_CUDA(cudaEventRecord(sl.ev_h, sl.st_main));
     return G16_OK;
   }
   int witness_map(const uint64_t* z, uint32_t flags, uint64_t* h) override {
     if (!have_circuit) return fail(G16_ERR_BAD_ARGUMENT, "no circuit resident");
     if (!z || !h) return fail(G16_ERR_BAD_ARGUMENT, "null buffer");
+    if (S0.busy) return fail(G16_ERR_BAD_ARGUMENT, "slot 0 has a proof in flight");
     G16_CUDA(cudaSetDevice(device));
-    int rc = enqueue_witness_map(z, flags);
+    int rc = enqueue_witness_map(S0, z, flags);
     if (rc) return rc;
-    G16_CUDA(cudaMemcpyAsync(h, d_h.p, (size_t)32 << L, cudaMemcpyDeviceToHost, st_main));
-    G16_CUDA(cudaStreamSynchronize(st_main));
+    G16_CUDA(cudaMemcpyAsync(h, S0.d_h.p, (size_t)32 << L, cudaMemcpyDeviceToHost, S0.st_main));
+    G16_CUDA(cudaStreamSynchronize(S0.st_main));
     return G16_OK;
   }
 
-  struct Partials { P1 h, l, a, b1; P2 b2; };
-  int run_msms(const uint64_t* r, const uint64_t* z, uint32_t flags, Partials& out) {
+  // Asynchronous half of a proof: everything is enqueued on the slot's streams, nothing is waited for.
+  // s may be null (partial proof: the (r, s)-only scalar multiplications are skipped).
+  int submit(Slot& sl, const uint64_t* r, const uint64_t* s, const uint64_t* z, uint32_t flags) {
     if (!have_circuit || !have_pk) return fail(G16_ERR_BAD_ARGUMENT, "circuit and proving key must be resident");
     if (!r || !z) return fail(G16_ERR_BAD_ARGUMENT, "null buffer");
+    if (sl.busy) return fail(G16_ERR_BAD_ARGUMENT, "slot already has a proof in flight (g16_prove_wait first)");
     G16_CUDA(cudaSetDevice(device));
-    const unsigned long long l0 = ctr.launches + ntt_launches;
-    const bool serial = (flags & G16_SERIAL_MSMS) != 0;
-    const bool r_zero = load_fr(r).is_zero();
-    int rc = enqueue_witness_map(z, flags);
+    sl.launches0 = ctr.launches + ntt_launches;
+    sl.serial = (flags & G16_SERIAL_MSMS) != 0;
+    sl.r = load_fr(r);
+    sl.have_s = s != nullptr;
+    if (s) sl.s = load_fr(s);
+    const bool r_zero = sl.r.is_zero();
+    if (sl.have_s) {
+      if (sl.helper.joinable()) sl.helper.join();
+      sl.helper = std::thread([this, &sl]() { sl.fx = fixed_muls(sl.r, sl.s); });
+    }
+    int rc = enqueue_witness_map(sl, z, flags);
     if (rc) return rc;
-    const uint32_t* zs = d_z.template as<uint32_t>();
-    const uint32_t* hs = d_h.template as<uint32_t>();
+    const uint32_t* zs = sl.d_z.template as<uint32_t>();
+    const uint32_t* hs = sl.d_h.template as<uint32_t>();
     // scalar sources (prover.rs:63-85): H <- h ; L <- aux ; A, B1, B2 <- input[1..] ++ aux
     const uint32_t* src[5] = {hs, zs + (size_t)num_inputs * 8, zs + 8, zs + 8, zs + 8};
-    MsmGeom geom[5];
-    bool run[5];
     for (int m = 0; m < 5; m++) {
       const uint64_t cnt = q[m].hi - q[m].lo;
-      geom[m] = q[m].geom;
-      run[m] = cnt > 0 && !(m == M_B1 && r_zero);                        // prover.rs:98: B in G1 skipped when r == 0
-      tm.msm_pairs[m] = run[m] ? cnt : 0;
+      sl.geom[m] = q[m].geom;
+      sl.run[m] = cnt > 0 && !(m == M_B1 && r_zero);                     // prover.rs:98: B in G1 skipped when r == 0
+      sl.tm.msm_pairs[m] = sl.run[m] ? cnt : 0;
     }
     const int order[5] = {M_L, M_A, M_B1, M_B2, M_H};                    // H last: it waits for the witness map
     for (int oi = 0; oi < 5; oi++) {
       const int m = order[oi];
-      cudaStream_t st = serial ? st_main : st_msm[m];
-      if (!serial) G16_CUDA(cudaStreamWaitEvent(st, m == M_H ? ev_h : ev_z, 0));
-      G16_CUDA(cudaEventRecord(ev_m0[m], st));
-      if (run[m]) {
+      cudaStream_t st = sl.serial ? sl.st_main : sl.st_msm[m];
+      if (!sl.serial) G16_CUDA(cudaStreamWaitEvent(st, m == M_H ? sl.ev_h : sl.ev_z, 0));
+      G16_CUDA(cudaEventRecord(sl.ev_m0[m], st));
+      if (sl.run[m]) {
         const uint32_t* sc = src[m] + q[m].lo * 8;
         cudaError_t e;
-        if (m == M_B2) e = msm_enqueue<Fq2, Fr>(st, ws2, geom[m], q[m].bases.template as<A2>(), q[m].mask.template as<uint8_t>(), sc, true, &ctr, ev_a0[m], ev_a1[m]);
-        else e = msm_enqueue<Fq, Fr>(st, ws1[m], geom[m], q[m].bases.template as<A1>(), q[m].mask.template as<uint8_t>(), sc, true, &ctr, ev_a0[m], ev_a1[m]);
+        if (m == M_B2) e = msm_enqueue<Fq2, Fr>(st, sl.ws2, sl.geom[m], q[m].bases.template as<A2>(), q[m].mask.template as<uint8_t>(), sc, true, &ctr, sl.ev_a0[m], sl.ev_a1[m]);
+        else e = msm_enqueue<Fq, Fr>(st, sl.ws1[m], sl.geom[m], q[m].bases.template as<A1>(), q[m].mask.template as<uint8_t>(), sc, true, &ctr, sl.ev_a0[m], sl.ev_a1[m]);
         if (e != cudaSuccess) return fail(G16_ERR_CUDA, std::string("msm_enqueue: ") + cudaGetErrorString(e));
       }
-      G16_CUDA(cudaEventRecord(ev_m1[m], st));
+      G16_CUDA(cudaEventRecord(sl.ev_m1[m], st));
     }
-    // Finish each MSM on the host (leaf sums of the bucket reduction, Horner) as soon as its stream drains, one host
-    // thread per MSM: the host work of the early finishers overlaps the GPU work still in flight.
-    if (serial) G16_CUDA(cudaStreamSynchronize(st_main));
+    sl.busy = true;
+    return G16_OK;
+  }
+  // Synchronous half: wait for the slot's streams, finish every MSM on the host (leaf sums of the bucket reduction,
+  // Horner) as soon as its stream drains, one host thread per MSM.
+  int wait_partials(Slot& sl, Partials& out) {
+    if (!sl.busy) return fail(G16_ERR_BAD_ARGUMENT, "no proof in flight in this slot");
+    G16_CUDA(cudaSetDevice(device));
+    sl.busy = false;
+    auto t0 = std::chrono::steady_clock::now();
+    if (sl.serial) G16_CUDA(cudaStreamSynchronize(sl.st_main));
     {
-      auto t0 = std::chrono::steady_clock::now();
       cudaError_t errs[5] = {cudaSuccess, cudaSuccess, cudaSuccess, cudaSuccess, cudaSuccess};
       P1* outs1[4] = {&out.h, &out.l, &out.a, &out.b1};
       std::thread th[5];
       for (int m = 0; m < 5; m++) {
         th[m] = std::thread([&, m]() {
           cudaSetDevice(device);
-          if (!serial) errs[m] = cudaStreamSynchronize(st_msm[m]);
+          if (!sl.serial) errs[m] = cudaStreamSynchronize(sl.st_msm[m]);
           if (errs[m] != cudaSuccess) return;
-          if (m == M_B2) out.b2 = run[m] ? msm_finish<Fq2>(ws2, geom[m]) : P2::inf();
-          else *outs1[m] = run[m] ? msm_finish<Fq>(ws1[m], geom[m]) : P1::inf();
+          if (m == M_B2) out.b2 = sl.run[m] ? msm_finish<Fq2>(sl.ws2, sl.geom[m]) : P2::inf();
+          else *outs1[m] = sl.run[m] ? msm_finish<Fq>(sl.ws1[m], sl.geom[m]) : P1::inf();
         });
       }
       for (auto& t : th) t.join();
       for (int m = 0; m < 5; m++)
         if (errs[m] != cudaSuccess) return fail(G16_ERR_CUDA, std::string("msm stream sync: ") + cudaGetErrorString(errs[m]));
-      G16_CUDA(cudaStreamSynchronize(st_main));
-      tm.host_finish_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      G16_CUDA(cudaStreamSynchronize(sl.st_main));
     }
+    sl.tm.host_finish_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     // timings
     float ms = 0, tot = 0;
-    cudaEventElapsedTime(&tm.h2d_ms, ev_start, ev_z);
-    cudaEventElapsedTime(&tm.witness_map_ms, ev_z, ev_h);
-    cudaEventElapsedTime(&tot, ev_start, ev_h);
+    cudaEventElapsedTime(&sl.tm.h2d_ms, sl.ev_start, sl.ev_z);
+    cudaEventElapsedTime(&sl.tm.witness_map_ms, sl.ev_z, sl.ev_h);
+    cudaEventElapsedTime(&tot, sl.ev_start, sl.ev_h);
     for (int m = 0; m < 5; m++) {
-      cudaEventElapsedTime(&tm.msm_ms[m], ev_m0[m], ev_m1[m]);
-      tm.msm_accum_ms[m] = 0;
-      if (run[m]) cudaEventElapsedTime(&tm.msm_accum_ms[m], ev_a0[m], ev_a1[m]);
-      cudaEventElapsedTime(&ms, ev_start, ev_m1[m]);
+      cudaEventElapsedTime(&sl.tm.msm_ms[m], sl.ev_m0[m], sl.ev_m1[m]);
+      sl.tm.msm_accum_ms[m] = 0;
+      if (sl.run[m]) cudaEventElapsedTime(&sl.tm.msm_accum_ms[m], sl.ev_a0[m], sl.ev_a1[m]);
+      cudaEventElapsedTime(&ms, sl.ev_start, sl.ev_m1[m]);
       if (ms > tot) tot = ms;
     }
-    tm.total_ms = tot;
-    tm.launches = ctr.launches + ntt_launches - l0;
-    tm.d2h_bytes = 0;
+    sl.tm.total_ms = tot;
+    sl.tm.launches = ctr.launches + ntt_launches - sl.launches0;
+    sl.tm.d2h_bytes = 0;
     for (int m = 0; m < 5; m++)
-      if (run[m]) tm.d2h_bytes += (m == M_B2 ? ws2.plan.leaf_pts * sizeof(P2) : ws1[m].plan.leaf_pts * sizeof(P1)) * geom[m].ne;
+      if (sl.run[m]) sl.tm.d2h_bytes += (m == M_B2 ? sl.ws2.plan.leaf_pts * sizeof(P2) : sl.ws1[m].plan.leaf_pts * sizeof(P1)) * sl.geom[m].ne;
+    tm = sl.tm;
     return G16_OK;
   }
   void store_partials(uint64_t* p, const Partials& x) {
@@ -656,15 +709,27 @@ struct Engine : IEngine {
   }
   int prove_partial(const uint64_t* r, const uint64_t* z, uint32_t flags, uint64_t* partial) override {
     if (!partial) return fail(G16_ERR_BAD_ARGUMENT, "null buffer");
+    int rc = submit(S0, r, nullptr, z, flags);
+    if (rc) return rc;
     Partials x;
-    int rc = run_msms(r, z, flags, x);
+    if ((rc = wait_partials(S0, x))) return rc;
+    store_partials(partial, x);
+    return G16_OK;
+  }
+  int partial_submit(int slot, const uint64_t* r, const uint64_t* z, uint32_t flags) override {
+    if (slot < 0 || slot >= NSLOTS) return fail(G16_ERR_BAD_ARGUMENT, "bad slot");
+    return submit(slots[slot], r, nullptr, z, flags);
+  }
+  int partial_wait(int slot, uint64_t* partial) override {
+    if (slot < 0 || slot >= NSLOTS || !partial) return fail(G16_ERR_BAD_ARGUMENT, "bad slot / null buffer");
+    Partials x;
+    int rc = wait_partials(slots[slot], x);
     if (rc) return rc;
     store_partials(partial, x);
     return G16_OK;
   }
   // prover.rs:76-131 on the host.  The four scalar multiplications that depend only on (r, s) and the key are computed
   // by a helper thread while the GPU works (fixed_muls); the two that need MSM results follow in assemble().
-  struct FixedMuls { P1 r_d1, s_d1, rs_d1; P2 s_d2; };
   FixedMuls fixed_muls(const Fr& r, const Fr& s) const {
     uint32_t rk[8], sk[8], rsk[8];
     fr_to_canon(r, rk);
@@ -712,22 +777,32 @@ struct Engine : IEngine {
     store_a1(proof + 6 * NQ64, g_c.to_affine());
     return G16_OK;
   }
-  int prove(const uint64_t* r, const uint64_t* s, const uint64_t* z, uint32_t flags, uint64_t* proof) override {
-    if (!s || !proof) return fail(G16_ERR_BAD_ARGUMENT, "null buffer");
+  int prove_submit(int slot, const uint64_t* r, const uint64_t* s, const uint64_t* z, uint32_t flags) override {
+    if (slot < 0 || slot >= NSLOTS) return fail(G16_ERR_BAD_ARGUMENT, "bad slot");
+    if (!s) return fail(G16_ERR_BAD_ARGUMENT, "null buffer");
     if (world != 1) return fail(G16_ERR_BAD_ARGUMENT, "key is sharded: use g16_prove_partial + g16_prove_assemble");
-    if (!r) return fail(G16_ERR_BAD_ARGUMENT, "null buffer");
+    return submit(slots[slot], r, s, z, flags);
+  }
+  int prove_wait(int slot, uint64_t* proof) override {
+    if (slot < 0 || slot >= NSLOTS || !proof) return fail(G16_ERR_BAD_ARGUMENT, "bad slot / null buffer");
+    Slot& sl = slots[slot];
     Partials x;
-    const Fr rr = load_fr(r), ss = load_fr(s);
-    FixedMuls fx;
-    std::thread helper([&]() { fx = fixed_muls(rr, ss); });
-    int rc = run_msms(r, z, flags, x);
-    helper.join();
+    int rc = wait_partials(sl, x);
+    if (sl.helper.joinable()) sl.helper.join();
     if (rc) return rc;
+    if (!sl.have_s) return fail(G16_ERR_BAD_ARGUMENT, "slot holds a partial proof (use g16_prove_partial_wait)");
     auto t0 = std::chrono::steady_clock::now();
-    rc = assemble(rr, ss, x, fx, proof);
-    tm.host_finish_ms += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    tm.d2h_bytes += 8 * NQ64 * 8;
+    rc = assemble(sl.r, sl.s, x, sl.fx, proof);
+    sl.tm.host_finish_ms += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    sl.tm.d2h_bytes += 8 * NQ64 * 8;
+    tm = sl.tm;
     return rc;
+  }
+  int prove(const uint64_t* r, const uint64_t* s, const uint64_t* z, uint32_t flags, uint64_t* proof) override {
+    if (!proof) return fail(G16_ERR_BAD_ARGUMENT, "null buffer");
+    int rc = prove_submit(0, r, s, z, flags);
+    if (rc) return rc;
+    return prove_wait(0, proof);
   }
   int prove_assemble(const uint64_t* r, const uint64_t* s, const uint64_t* partials, uint32_t nparts, uint64_t* proof) override {
     if (!have_pk) return fail(G16_ERR_BAD_ARGUMENT, "no proving key resident");

@@ -40,6 +40,18 @@ class ShardedProver:
         self.g.load_proving_key(pk, rank, world)
         self._partial = np.zeros(self.g.partial_limbs(), dtype=np.uint64)
 
+    # pipelined form: submit(slot) returns at once; finish(slot) waits, gathers and assembles.  Submitting proof i+1
+    # before finishing proof i overlaps the all_gather / host assembly of one proof with the GPU work of the next.
+    def submit(self, slot: int, r, z_ptr: int, flags: int = 0):
+        self._r_keep = getattr(self, "_r_keep", {})
+        self._r_keep[slot] = self.g._fr_arg(r)
+        self.g.prove_partial_submit_raw(slot, self._r_keep[slot], z_ptr, flags)
+
+    def finish(self, slot: int, r, s):
+        self.g.prove_partial_wait_raw(slot, self._partial)
+        allp = all_gather_partials(self._partial, self.device) if self.world > 1 else self._partial[None, :]
+        return self.g.prove_assemble(self.g._fr_arg(r), self.g._fr_arg(s), allp)
+
     def prove(self, r, s, z_ptr: int, flags: int = 0):
         """r, s: Montgomery limbs; z_ptr: address of the full assignment (host or device per `flags`)."""
         rl = self.g._fr_arg(r)

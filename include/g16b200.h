@@ -135,6 +135,17 @@ int g16_prove_partial(g16_ctx* ctx, const uint64_t* r, const uint64_t* full_assi
                       uint64_t* partial_out);
 int g16_prove_assemble(g16_ctx* ctx, const uint64_t* r, const uint64_t* s, const uint64_t* partials,
                        uint32_t nparts, uint64_t* proof_out);
+/* Pipelined proving: a context owns two proof slots (0 and 1), each with its own streams and work buffers.
+ * g16_prove_submit enqueues a whole proof asynchronously and returns; g16_prove_wait blocks until that slot's GPU
+ * work is done, finishes on the host and writes the proof.  Submitting proof i+1 before waiting for proof i lets
+ * the latency-bound tail of one proof overlap the bulk of the next (g16_prove == submit + wait on slot 0).
+ * The host buffers passed to submit (r, s, and the assignment unless G16_ASSIGNMENT_ON_DEVICE) must stay valid
+ * until the matching wait.  The *_partial_* pair is the same for the sharded path. */
+int g16_prove_submit(g16_ctx* ctx, int slot, const uint64_t* r, const uint64_t* s, const uint64_t* full_assignment,
+                     uint32_t flags);
+int g16_prove_wait(g16_ctx* ctx, int slot, uint64_t* proof_out);
+int g16_prove_partial_submit(g16_ctx* ctx, int slot, const uint64_t* r, const uint64_t* full_assignment, uint32_t flags);
+int g16_prove_partial_wait(g16_ctx* ctx, int slot, uint64_t* partial_out);
 /* limbs per partial record: 4*2*N64 + 4*N64 */
 int g16_partial_limbs(const g16_ctx* ctx);
 

@@ -133,7 +133,7 @@ struct Engine : IEngine {
   // entries per level-0 thread, from the number of resident accumulation threads of this device
   int sm_count = 148;
   MsmGeom with_k0(MsmGeom g, bool g2) const {
-    g.k0 = msm_pick_k0(g.max_entries, (uint64_t)sm_count * 128 * (g2 ? 2 : 3));
+    g.k0 = msm_pick_k0(g.max_entries, (uint64_t)sm_count * 128 * (g2 ? 2 : 3), g2 ? 16 : 8);
     return g;
   }
   template <class F>
@@ -650,6 +650,7 @@ struct Engine : IEngine {
       }
       G16_CUDA(cudaEventRecord(sl.ev_m1[m], st));
     }
+    sl.launches0 = ctr.launches + ntt_launches - sl.launches0;   // kernels launched for this proof
     sl.busy = true;
     return G16_OK;
   }
@@ -693,7 +694,7 @@ struct Engine : IEngine {
       if (ms > tot) tot = ms;
     }
     sl.tm.total_ms = tot;
-    sl.tm.launches = ctr.launches + ntt_launches - sl.launches0;
+    sl.tm.launches = sl.launches0;
     sl.tm.d2h_bytes = 0;
     for (int m = 0; m < 5; m++)
       if (sl.run[m]) sl.tm.d2h_bytes += (m == M_B2 ? sl.ws2.plan.leaf_pts * sizeof(P2) : sl.ws1[m].plan.leaf_pts * sizeof(P1)) * sl.geom[m].ne;

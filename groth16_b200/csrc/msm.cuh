@@ -40,9 +40,9 @@ struct MsmGeom {
 static constexpr int MSM_K0_MAX = 64;
 // Entries per thread so that the level-0 grid is at least ~2.5 waves of `resident_threads` (small MSMs, e.g. the per-rank
 // shards of a multi-GPU proof, would otherwise run as a fraction of one wave: time = one 64-entry chunk regardless of size).
-inline int msm_pick_k0(uint64_t max_entries, uint64_t resident_threads) {
+inline int msm_pick_k0(uint64_t max_entries, uint64_t resident_threads, int k0_min) {
   int k0 = MSM_K0_MAX;
-  while (k0 > 8 && max_entries / k0 < resident_threads * 5 / 2) k0 >>= 1;
+  while (k0 > k0_min && max_entries / k0 < resident_threads * 2) k0 >>= 1;
   return k0;
 }
 inline int msm_pick_c(uint64_t n) {

@@ -113,7 +113,7 @@ struct Engine : IEngine {
   struct Query {
     DevBuf bases, mask;   // bases: geom.copies * (hi - lo) affine points, copy-major (copy j = 2^(c*ne*j) * P)
     uint64_t pairs = 0;   // full MSM length
-    uint64_t lo = 0, hi = 0;
+    uint64_t lo = 0, hi = 0;   // this rank owns pairs lo, lo + world, lo + 2 world, ... : hi - lo of them (lo = rank)
     MsmGeom geom{};
   } q[5];
   // MSM tuning knobs (environment: G16_MSM_C, G16_MSM_NE, G16_MSM_MAXCOPIES)
@@ -333,7 +333,7 @@ struct Engine : IEngine {
       G16_CUDA(cudaMemcpyAsync(ds.p, scalars, n * 32, cudaMemcpyHostToDevice, S0.st_main));
       G16_CUDA(msm_prepare_query<F>(S0.st_main, db.template as<Affine<F>>(), (uint32_t)n, 1, 0, dm.template as<uint8_t>()));
       const MsmGeom g = with_k0(msm_geom(n, FR_BITS, cfg_c, 0), sizeof(F) > 48);   // caller-supplied bases: no precomputed copies
-      cudaError_t e = msm_enqueue<F, Fr>(S0.st_main, ws, g, db.template as<Affine<F>>(), dm.template as<uint8_t>(), ds.template as<uint32_t>(), false, &ctr, nullptr, nullptr);
+      cudaError_t e = msm_enqueue<F, Fr>(S0.st_main, ws, g, db.template as<Affine<F>>(), dm.template as<uint8_t>(), ds.template as<uint32_t>(), 1, false, &ctr, nullptr, nullptr);
       if (e != cudaSuccess) { db.release(); ds.release(); dm.release(); return fail(G16_ERR_CUDA, std::string("msm_enqueue: ") + cudaGetErrorString(e)); }
       e = cudaStreamSynchronize(S0.st_main);
       db.release(); ds.release(); dm.release();
@@ -387,8 +387,11 @@ struct Engine : IEngine {
   // ---- proving key ----
   void shard(Query& x, uint64_t pairs) {
     x.pairs = pairs;
-    x.lo = pairs * rank / world;
-    x.hi = pairs * (rank + 1) / world;
+    // Interleaved (strided) split: rank k owns pairs k, k + world, ...  Contiguous ranges would be badly unbalanced
+    // whenever the density of a query varies with the variable index (early variables of a circuit are used more often).
+    const uint64_t cnt = pairs > rank ? (pairs - rank + world - 1) / world : 0;
+    x.lo = rank;
+    x.hi = rank + cnt;
     x.geom = with_k0(pick_geom(x.hi - x.lo), &x == &q[M_B2]);
   }
   template <class F>
@@ -398,7 +401,9 @@ struct Engine : IEngine {
     G16_CUDA(x.bases.reserve((size_t)x.geom.copies * cnt * sizeof(AT) + 16));
     if (cnt) {
       const size_t limbs = sizeof(AT) / 8;
-      G16_CUDA(cudaMemcpyAsync(x.bases.p, host_full + (skip_first + x.lo) * limbs, cnt * sizeof(AT), cudaMemcpyHostToDevice, S0.st_main));
+      // gather every world-th point of the full host array
+      G16_CUDA(cudaMemcpy2DAsync(x.bases.p, sizeof(AT), host_full + (skip_first + x.lo) * limbs, (size_t)world * sizeof(AT), sizeof(AT), cnt,
+                                 cudaMemcpyHostToDevice, S0.st_main));
     }
     return finish_query<F>(x);
   }
@@ -642,10 +647,10 @@ struct Engine : IEngine {
       if (!sl.serial) G16_CUDA(cudaStreamWaitEvent(st, m == M_H ? sl.ev_h : sl.ev_z, 0));
       G16_CUDA(cudaEventRecord(sl.ev_m0[m], st));
       if (sl.run[m]) {
-        const uint32_t* sc = src[m] + q[m].lo * 8;
+        const uint32_t* sc = src[m] + q[m].lo * 8;   // first owned scalar; the digit kernel strides by `world`
         cudaError_t e;
-        if (m == M_B2) e = msm_enqueue<Fq2, Fr>(st, sl.ws2, sl.geom[m], q[m].bases.template as<A2>(), q[m].mask.template as<uint8_t>(), sc, true, &ctr, sl.ev_a0[m], sl.ev_a1[m]);
-        else e = msm_enqueue<Fq, Fr>(st, sl.ws1[m], sl.geom[m], q[m].bases.template as<A1>(), q[m].mask.template as<uint8_t>(), sc, true, &ctr, sl.ev_a0[m], sl.ev_a1[m]);
+        if (m == M_B2) e = msm_enqueue<Fq2, Fr>(st, sl.ws2, sl.geom[m], q[m].bases.template as<A2>(), q[m].mask.template as<uint8_t>(), sc, world, true, &ctr, sl.ev_a0[m], sl.ev_a1[m]);
+        else e = msm_enqueue<Fq, Fr>(st, sl.ws1[m], sl.geom[m], q[m].bases.template as<A1>(), q[m].mask.template as<uint8_t>(), sc, world, true, &ctr, sl.ev_a0[m], sl.ev_a1[m]);
         if (e != cudaSuccess) return fail(G16_ERR_CUDA, std::string("msm_enqueue: ") + cudaGetErrorString(e));
       }
       G16_CUDA(cudaEventRecord(sl.ev_m1[m], st));

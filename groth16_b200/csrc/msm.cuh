@@ -74,7 +74,7 @@ inline MsmGeom msm_geom(uint64_t n, int scalar_bits, int c_override = 0, int ne_
 // ------------------------------------------------------------------------------------------------
 // Signed-digit recoding of a canonical scalar k < 2^bits:  k = sum_w d_w 2^(c w), d_w in [-2^(c-1), 2^(c-1)].
 template <class FrF, bool SCATTER>
-__global__ void __launch_bounds__(256) msm_digits(const uint32_t* __restrict__ scalars, int scalars_mont,
+__global__ void __launch_bounds__(256) msm_digits(const uint32_t* __restrict__ scalars, uint32_t scalar_stride, int scalars_mont,
                                                   const uint8_t* __restrict__ skip, MsmGeom g,
                                                   uint32_t* __restrict__ counters,  // COUNT: histogram; SCATTER: cursors
                                                   uint32_t* __restrict__ sidx, uint32_t* __restrict__ skey) {
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) msm_digits(const uint32_t* __restrict__ s
   bool live = i < g.n;
   FrF s = FrF::zero();
   if (live) {
-    const uint4* p = reinterpret_cast<const uint4*>(scalars) + (size_t)i * 2;
+    const uint4* p = reinterpret_cast<const uint4*>(scalars) + (size_t)i * scalar_stride * 2;
     uint4 lo = __ldg(p), hi = __ldg(p + 1);
     s.v[0] = lo.x; s.v[1] = lo.y; s.v[2] = lo.z; s.v[3] = lo.w;
     s.v[4] = hi.x; s.v[5] = hi.y; s.v[6] = hi.z; s.v[7] = hi.w;
@@ -590,11 +590,11 @@ struct MsmCounters {  // launch bookkeeping for bench.py's gpu_launches
 };
 
 // Enqueue one MSM on `st`.  d_bases holds g.copies * g.n affine points (copy-major); d_scalars / d_skip are device
-// pointers; the leaf arrays of the bucket reduction land in ws.h_leaf once the stream is synchronised (msm_finish).
+// pointers, pair i uses the scalar at d_scalars + 8 * i * scalar_stride (stride = world size for a sharded key); the leaf arrays of the bucket reduction land in ws.h_leaf once the stream is synchronised (msm_finish).
 template <class F, class FrF>
 cudaError_t msm_enqueue(cudaStream_t st, MsmWorkspace<F>& ws, const MsmGeom& g, const Affine<F>* d_bases,
-                        const uint8_t* d_skip, const uint32_t* d_scalars, bool scalars_mont, MsmCounters* ctr,
-                        cudaEvent_t ev_acc0, cudaEvent_t ev_acc1) {
+                        const uint8_t* d_skip, const uint32_t* d_scalars, uint32_t scalar_stride, bool scalars_mont,
+                        MsmCounters* ctr, cudaEvent_t ev_acc0, cudaEvent_t ev_acc1) {
   cudaError_t e;
   if (g.n == 0) return cudaSuccess;
   if ((e = ws.prepare(g)) != cudaSuccess) return e;
@@ -610,12 +610,12 @@ cudaError_t msm_enqueue(cudaStream_t st, MsmWorkspace<F>& ws, const MsmGeom& g, 
   cudaMemsetAsync(pending, 0, 64 * 4, st);
   cudaMemsetAsync(buckets, 0, (size_t)g.nkeys * sizeof(XYZZ<F>), st);
   const uint32_t nb = (g.n + 255) / 256;
-  msm_digits<FrF, false><<<nb, 256, 0, st>>>(d_scalars, scalars_mont ? 1 : 0, d_skip, g, counters, nullptr, nullptr);
+  msm_digits<FrF, false><<<nb, 256, 0, st>>>(d_scalars, scalar_stride, scalars_mont ? 1 : 0, d_skip, g, counters, nullptr, nullptr);
   const uint32_t sb = (g.nkeys + SCAN_BLOCK - 1) / SCAN_BLOCK;
   msm_scan_blocks<<<sb, 1024, 0, st>>>(counters, g.nkeys, offsets, blocktot);
   msm_scan_tops<<<1, 1024, 0, st>>>(blocktot, sb, offsets + g.nkeys);
   msm_scan_fix<<<sb, 1024, 0, st>>>(offsets, g.nkeys, blocktot, counters);
-  msm_digits<FrF, true><<<nb, 256, 0, st>>>(d_scalars, scalars_mont ? 1 : 0, d_skip, g, counters, sidx, skey);
+  msm_digits<FrF, true><<<nb, 256, 0, st>>>(d_scalars, scalar_stride, scalars_mont ? 1 : 0, d_skip, g, counters, sidx, skey);
   nl += 5;
   // level 0
   const uint64_t T0 = (g.max_entries + g.k0 - 1) / g.k0;
@@ -806,7 +806,7 @@ cudaError_t fb_batch_mul(cudaStream_t st, const Affine<F>& gen, const FrF* d_sca
 // declares them `extern template` (keeps ptxas work parallel across make jobs).
 #define G16_MSM_TEMPLATES(X, F, FrF)                                                                                     \
   X cudaError_t msm_enqueue<F, FrF>(cudaStream_t, MsmWorkspace<F>&, const MsmGeom&, const Affine<F>*, const uint8_t*,    \
-                                    const uint32_t*, bool, MsmCounters*, cudaEvent_t, cudaEvent_t);                      \
+                                    const uint32_t*, uint32_t, bool, MsmCounters*, cudaEvent_t, cudaEvent_t);            \
   X cudaError_t msm_prepare_query<F>(cudaStream_t, Affine<F>*, uint32_t, int, int, uint8_t*);                            \
   X cudaError_t fb_batch_mul<F, FrF>(cudaStream_t, const Affine<F>&, const FrF*, uint64_t, Affine<F>*, XYZZ<F>*);
 

@@ -1,7 +1,7 @@
 """Multi-GPU plumbing (one process per GPU, torch.distributed): SURVEY.md section 8e.
 
-Every MSM's (scalar, base) pairs are split by contiguous index range over the ranks; each rank's context keeps only its
-range of every query resident (g16_pk_load(rank, world)).  Per proof a rank computes five partial sums
+Every MSM's (scalar, base) pairs are dealt round-robin to the ranks (pair i -> rank i mod world); each rank's context keeps
+only its share of every query resident (g16_pk_load(rank, world)).  Per proof a rank computes five partial sums
 (g16_prove_partial), the 5 affine points per rank are all-gathered (NCCL on GPUs, gloo in the CPU tests) and every rank
 assembles the same proof (g16_prove_assemble).  EC addition is exactly associative and commutative, so the proof is
 bit-identical for any world size; NCCL has no user-defined reduction for curve points, hence gather-then-add.
@@ -11,9 +11,11 @@ from __future__ import annotations
 import numpy as np
 
 
-def shard_range(pairs: int, rank: int, world: int):
-    """Index range of an MSM of `pairs` pairs owned by `rank` -- must match Engine::shard in csrc/engine.cuh."""
-    return pairs * rank // world, pairs * (rank + 1) // world
+def shard_indices(pairs: int, rank: int, world: int) -> slice:
+    """Pairs of an MSM of `pairs` pairs owned by `rank`: rank, rank + world, ... -- must match Engine::shard in
+    csrc/engine.cuh.  The split is interleaved rather than by contiguous range because the density of a query usually
+    varies with the variable index (early variables are used more often): contiguous ranges would be unbalanced."""
+    return slice(rank, pairs, world)
 
 
 def all_gather_partials(partial: np.ndarray, device=None) -> np.ndarray:

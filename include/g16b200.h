@@ -88,7 +88,7 @@ int g16_circuit_load(g16_ctx* ctx, uint32_t num_inputs /* instance variables inc
 
 /* ---- proving key: data_structures.rs:126-143.  Query arrays are the FULL ark vectors (a_query[0] included).
  * With world > 1 the context keeps only the index range of every query owned by `rank`:
- * contiguous split of each MSM's (base, scalar) pairs. */
+ * round-robin split of each MSM's (base, scalar) pairs: pair i belongs to rank i mod world. */
 typedef struct {
   const uint64_t* a_query;    uint64_t a_len;     /* G1, num_inputs + num_witness      (generator.rs:155) */
   const uint64_t* b_g1_query; uint64_t b_g1_len;  /* G1, same length                   (generator.rs:161) */

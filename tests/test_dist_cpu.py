@@ -1,4 +1,4 @@
-"""World-size-2 gloo test (CPU) of the multi-GPU plumbing: index-range sharding + all_gather of partial points +
+"""World-size-2 gloo test (CPU) of the multi-GPU plumbing: round-robin sharding + all_gather of partial points +
 order-independent summation reproduce the unsharded MSM.  The per-rank partial MSMs are computed
 by the CPU oracle here; on GPUs the same plumbing carries g16_prove_partial outputs (tests/test_gpu_parity.py
 ::test_sharded_prove_equals_single checks the CUDA side, bench.py --gpus N the NCCL side)."""
@@ -14,7 +14,7 @@ import torch.multiprocessing as mp
 import orc
 import pyref as P
 from groth16_b200 import CurveCodec, get_curve
-from groth16_b200.dist import all_gather_partials, shard_range
+from groth16_b200.dist import all_gather_partials, shard_indices
 
 
 def _free_port():
@@ -28,8 +28,8 @@ def _free_port():
 def _worker(rank, world, port, bases, scalars, nq, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    lo, hi = shard_range(bases.shape[0], rank, world)
-    part = orc.msm_g1(1, nq, bases[lo:hi], scalars[lo:hi], threads=1)   # normalised projective X||Y||Z
+    sel = shard_indices(bases.shape[0], rank, world)
+    part = orc.msm_g1(1, nq, np.ascontiguousarray(bases[sel]), np.ascontiguousarray(scalars[sel]), threads=1)   # X||Y||Z
     allp = all_gather_partials(part)
     if rank == 0:
         q.put(allp)
@@ -62,5 +62,5 @@ def test_sharded_msm_over_gloo():
     for r in range(world):
         total = cx.G1.add(total, cd.dec_proj_g1(allp[r]))
     assert total == cx.G1.msm_naive(pts, sc)
-    # ranges tile [0, n) exactly, like Engine::shard
-    assert [shard_range(n, r, 3) for r in range(3)] == [(0, 12), (12, 24), (24, 37)]
+    # the shares tile [0, n) exactly, like Engine::shard
+    assert sorted(i for r in range(3) for i in range(n)[shard_indices(n, r, 3)]) == list(range(n))

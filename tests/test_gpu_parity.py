@@ -202,7 +202,7 @@ def test_prove_mimc(curve):
 
 
 def test_sharded_prove_equals_single():
-    """splitting every query by index range over `world` ranks and summing the partial points gives
+    """dealing every query round-robin over `world` ranks and summing the partial points gives
     the same proof bit for bit (here: 3 ranks emulated sequentially on one GPU)."""
     curve = "bn254"
     c = P.CURVES[curve]

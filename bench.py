@@ -40,11 +40,11 @@ def parse():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--cpu-threads", type=int, default=0, help="threads for the CPU arm / cpu_baseline (0 = all)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--inflight", type=int, default=0, choices=[0, 1, 2],
-                    help="proofs in flight per GPU: 2 = software pipeline over the two proof slots of a context "
-                         "(g16_prove_submit / g16_prove_wait), 1 = strictly one proof at a time, 0 = auto: 2 for one GPU / "
-                         "replicas (+2%% throughput), 1 for the sharded mode (measured: the NCCL gather of proof i then "
-                         "queues behind the bulk kernels of proof i+1 and the step gets slower)")
+    ap.add_argument("--inflight", type=int, default=1, choices=[1, 2],
+                    help="proofs in flight per GPU: 1 = one proof at a time (default); 2 = software pipeline over the two "
+                         "proof slots of a context (g16_prove_submit / g16_prove_wait).  Measured on B200: one proof already "
+                         "keeps the multiplier pipes busy (5 MSM streams), so pipelining gains at most ~2%% and can lose when "
+                         "two proofs' bulk kernels interleave (resident inputs) or an NCCL gather queues behind them")
     ap.add_argument("--mode", default="shard", choices=["shard", "replicas"],
                     help="N > 1: 'shard' splits every MSM of ONE proof over the GPUs (strong scaling, NCCL gather of partial "
                          "points); 'replicas' lets every GPU prove its own proofs (weak scaling, no communication; "
@@ -279,8 +279,6 @@ def run_cuda(a):
     pk = g.generate_parameters_with_qap(m, *TOXIC, G["g1"], G["g2"],
                                         export=((world > 1 and a.mode == "shard") or not a.no_cpu_baseline))
     replicas = world > 1 and a.mode == "replicas"
-    if a.inflight == 0:
-        a.inflight = 2 if (world == 1 or replicas) else 1
     sp = None
     if world > 1 and not replicas:
         from groth16_b200.dist import ShardedProver

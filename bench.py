@@ -26,7 +26,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "groth16_proofs_per_sec_bls12_381_2^20"
+def metric_name(a):
+    return f"groth16_proofs_per_sec_{a.curve}_2^{a.log_n}"
+
 
 
 def parse():
@@ -242,7 +244,7 @@ def run_reference(a):
     dt = time.time() - t0
     val = a.steps / dt
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": "proofs/s", "n_gpus": a.gpus, "steps": a.steps,
+        "impl": "reference", "metric": metric_name(a), "value": val, "unit": "proofs/s", "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u64 limbs (255-bit Fr / 381-bit Fq Montgomery integers)", "data": "synthetic",
         "config": {"workload": workload_name(a), "curve": a.curve, "log_n": a.log_n, "pk": kind_pk},
@@ -425,7 +427,7 @@ def run_cuda(a):
                    "sample": f"1 full proof of the same workload ({csec:.2f} s wall: witness map {tms[0]:.0f} ms, MSMs+assembly "
                              f"{tms[1]:.0f} ms), restated ark CPU path; proof bit-identical to the CUDA proof"}
         line = {
-            "metric": METRIC, "value": value, "unit": "proofs/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "metric": metric_name(a), "value": value, "unit": "proofs/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak" if replicas else "strong",
             "vs_baseline": None,
             "dtype": "u32 limbs (255-bit Fr / 381-bit Fq Montgomery integers)", "data": "synthetic",

@@ -53,6 +53,7 @@ SIGNATURES = [
     ("g16_prove", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
     ("g16_prove_partial", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
     ("g16_prove_assemble", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    ("g16_prove_assemble_prepare", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     ("g16_prove_submit", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     ("g16_prove_wait", C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     ("g16_prove_partial_submit", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32]),

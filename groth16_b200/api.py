@@ -323,6 +323,11 @@ class Groth16:
     def prove_partial_raw(self, r_limbs: np.ndarray, z_ptr, flags: int, out: np.ndarray):
         _check(self._lib.g16_prove_partial(self._ctx, _ptr(r_limbs), C.c_void_p(z_ptr), flags, _ptr(out)))
 
+    def prove_assemble_prepare(self, r, s):
+        """start the (r, s)-only scalar multiplications on a helper thread (overlaps GPU work and the gather)"""
+        self._asm_keep = (self._fr_arg(r), self._fr_arg(s))
+        _check(self._lib.g16_prove_assemble_prepare(self._ctx, _ptr(self._asm_keep[0]), _ptr(self._asm_keep[1])))
+
     def prove_assemble(self, r, s, partials: np.ndarray) -> Proof:
         rr, ss = self._fr_arg(r), self._fr_arg(s)
         pl = self._lib.g16_partial_limbs(self._ctx)

@@ -100,6 +100,10 @@ int g16_prove_assemble(g16_ctx* ctx, const uint64_t* r, const uint64_t* s, const
   CTX_OR_FAIL(ctx);
   return ctx->eng->prove_assemble(r, s, partials, nparts, proof_out);
 }
+int g16_prove_assemble_prepare(g16_ctx* ctx, const uint64_t* r, const uint64_t* s) {
+  CTX_OR_FAIL(ctx);
+  return ctx->eng->assemble_prepare(r, s);
+}
 int g16_prove_submit(g16_ctx* ctx, int slot, const uint64_t* r, const uint64_t* s, const uint64_t* full_assignment, uint32_t flags) {
   CTX_OR_FAIL(ctx);
   return ctx->eng->prove_submit(slot, r, s, full_assignment, flags);

@@ -48,6 +48,7 @@ struct IEngine {
   virtual int prove(const uint64_t* r, const uint64_t* s, const uint64_t* z, uint32_t flags, uint64_t* proof) = 0;
   virtual int prove_partial(const uint64_t* r, const uint64_t* z, uint32_t flags, uint64_t* partial) = 0;
   virtual int prove_assemble(const uint64_t* r, const uint64_t* s, const uint64_t* partials, uint32_t nparts, uint64_t* proof) = 0;
+  virtual int assemble_prepare(const uint64_t* r, const uint64_t* s) = 0;
   virtual int prove_submit(int slot, const uint64_t* r, const uint64_t* s, const uint64_t* z, uint32_t flags) = 0;
   virtual int prove_wait(int slot, uint64_t* proof) = 0;
   virtual int partial_submit(int slot, const uint64_t* r, const uint64_t* z, uint32_t flags) = 0;
@@ -192,6 +193,7 @@ struct Engine : IEngine {
     cudaSetDevice(device);
     for (Slot& sl : slots)
       if (sl.helper.joinable()) sl.helper.join();
+    if (asm_helper.joinable()) asm_helper.join();
     cudaDeviceSynchronize();
     dom.release();
     for (Slot& sl : slots) {
@@ -810,9 +812,26 @@ struct Engine : IEngine {
     if (rc) return rc;
     return prove_wait(0, proof);
   }
+  // Sharded path: the (r, s)-only scalar multiplications can be started before the partial sums exist
+  // (g16_prove_assemble_prepare), so that they overlap the GPU work and the gather; prove_assemble picks them up.
+  Fr asm_r, asm_s;
+  FixedMuls asm_fx;
+  bool asm_valid = false;
+  std::thread asm_helper;
+  int assemble_prepare(const uint64_t* r, const uint64_t* s) override {
+    if (!have_pk) return fail(G16_ERR_BAD_ARGUMENT, "no proving key resident");
+    if (!r || !s) return fail(G16_ERR_BAD_ARGUMENT, "null buffer");
+    if (asm_helper.joinable()) asm_helper.join();
+    asm_r = load_fr(r);
+    asm_s = load_fr(s);
+    asm_valid = true;
+    asm_helper = std::thread([this]() { asm_fx = fixed_muls(asm_r, asm_s); });
+    return G16_OK;
+  }
   int prove_assemble(const uint64_t* r, const uint64_t* s, const uint64_t* partials, uint32_t nparts, uint64_t* proof) override {
     if (!have_pk) return fail(G16_ERR_BAD_ARGUMENT, "no proving key resident");
     if (!r || !s || !partials || !proof || nparts == 0) return fail(G16_ERR_BAD_ARGUMENT, "null buffer");
+    if (asm_helper.joinable()) asm_helper.join();
     Partials x{P1::inf(), P1::inf(), P1::inf(), P1::inf(), P2::inf()};
     const int pl = partial_limbs();
     for (uint32_t i = 0; i < nparts; i++) {   // fixed rank order; the sum is order-independent anyway
@@ -824,6 +843,10 @@ struct Engine : IEngine {
       x.b2.madd(load_a2(p + 8 * NQ64));
     }
     const Fr rr = load_fr(r), ss = load_fr(s);
+    if (asm_valid && rr == asm_r && ss == asm_s) {
+      asm_valid = false;
+      return assemble(rr, ss, x, asm_fx, proof);
+    }
     return assemble(rr, ss, x, fixed_muls(rr, ss), proof);
   }
 };

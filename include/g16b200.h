@@ -135,6 +135,9 @@ int g16_prove_partial(g16_ctx* ctx, const uint64_t* r, const uint64_t* full_assi
                       uint64_t* partial_out);
 int g16_prove_assemble(g16_ctx* ctx, const uint64_t* r, const uint64_t* s, const uint64_t* partials,
                        uint32_t nparts, uint64_t* proof_out);
+/* Optional: start the (r, s)-only scalar multiplications of prover.rs:76,90,100,112 on a helper thread before the partial
+ * sums exist; the next g16_prove_assemble with the same (r, s) picks the result up instead of computing it inline. */
+int g16_prove_assemble_prepare(g16_ctx* ctx, const uint64_t* r, const uint64_t* s);
 /* Pipelined proving: a context owns two proof slots (0 and 1), each with its own streams and work buffers.
  * g16_prove_submit enqueues a whole proof asynchronously and returns; g16_prove_wait blocks until that slot's GPU
  * work is done, finishes on the host and writes the proof.  Submitting proof i+1 before waiting for proof i lets

@@ -18,34 +18,17 @@ def shard_indices(pairs: int, rank: int, world: int) -> slice:
     return slice(rank, pairs, world)
 
 
-_BUFS = {}
-
-
 def all_gather_partials(partial: np.ndarray, device=None) -> np.ndarray:
-    """partial: uint64 limbs of this rank's five partial points -> (world, limbs) array, rank order.
-    Buffers (pinned host staging + device tensors for NCCL) are allocated once per (device, size)."""
+    """partial: uint64 limbs of this rank's five partial points -> (world, limbs) array, rank order."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size()
-    n = int(partial.size)
-    key = (str(device), n, world)
-    if key not in _BUFS:
-        pin = device is not None
-        src_h = torch.zeros(n, dtype=torch.int64)
-        dst_h = torch.zeros(world * n, dtype=torch.int64)
-        if pin:
-            src_h, dst_h = src_h.pin_memory(), dst_h.pin_memory()
-        src_d = torch.zeros(n, dtype=torch.int64, device=device) if pin else src_h
-        dst_d = torch.zeros(world * n, dtype=torch.int64, device=device) if pin else dst_h
-        _BUFS[key] = (src_h, dst_h, src_d, dst_d)
-    src_h, dst_h, src_d, dst_d = _BUFS[key]
-    src_h.numpy().view(np.uint64)[:] = np.ascontiguousarray(partial, dtype=np.uint64).ravel()
+    t = torch.from_numpy(np.ascontiguousarray(partial, dtype=np.uint64).view(np.int64))
     if device is not None:
-        src_d.copy_(src_h, non_blocking=True)
-    dist.all_gather_into_tensor(dst_d, src_d)
-    if device is not None:
-        dst_h.copy_(dst_d, non_blocking=False)
-    return dst_h.numpy().view(np.uint64).reshape(world, -1).copy()
+        t = t.to(device)
+    out = torch.empty(world * t.numel(), dtype=torch.int64, device=t.device)
+    dist.all_gather_into_tensor(out, t)
+    return out.cpu().numpy().view(np.uint64).reshape(world, -1)
 
 
 class ShardedProver:
@@ -74,7 +57,6 @@ class ShardedProver:
     def prove(self, r, s, z_ptr: int, flags: int = 0):
         """r, s: Montgomery limbs; z_ptr: address of the full assignment (host or device per `flags`)."""
         rl = self.g._fr_arg(r)
-        self.g.prove_assemble_prepare(rl, s)     # (r, s)-only scalar multiplications overlap the GPU work
         self.g.prove_partial_raw(rl, z_ptr, flags, self._partial)
         allp = all_gather_partials(self._partial, self.device) if self.world > 1 else self._partial[None, :]
         return self.g.prove_assemble(rl, self.g._fr_arg(s), allp)

@@ -57,6 +57,7 @@ class ShardedProver:
     def prove(self, r, s, z_ptr: int, flags: int = 0):
         """r, s: Montgomery limbs; z_ptr: address of the full assignment (host or device per `flags`)."""
         rl = self.g._fr_arg(r)
+        self.g.prove_assemble_prepare(rl, s)     # (r, s)-only scalar multiplications overlap the GPU work and the gather
         self.g.prove_partial_raw(rl, z_ptr, flags, self._partial)
         allp = all_gather_partials(self._partial, self.device) if self.world > 1 else self._partial[None, :]
         return self.g.prove_assemble(rl, self.g._fr_arg(s), allp)

@@ -214,6 +214,10 @@ struct Engine : IEngine {
   int partial_limbs() const override { return 4 * 2 * NQ64 + 4 * NQ64; }
   uint32_t domain_log() const override { return (uint32_t)L; }
 
+  bool any_busy() const { return slots[0].busy || slots[1].busy; }
+#define G16_NOT_BUSY() \
+  if (any_busy()) return fail(G16_ERR_BAD_ARGUMENT, "a proof is in flight (g16_prove_wait / g16_prove_partial_wait it first)")
+
   // ---- small host helpers ----
   static Fr load_fr(const uint64_t* p) { Fr r; memcpy(r.v, p, sizeof(r.v)); return r; }
   static A1 load_a1(const uint64_t* p) { A1 r; memcpy(&r.x, p, sizeof(Fq)); memcpy(&r.y, p + NQ64, sizeof(Fq)); return r; }
@@ -266,6 +270,7 @@ struct Engine : IEngine {
   // ---- NTT API ----
   int ntt(uint32_t log_n, int inverse, int coset, uint64_t* inout) override {
     if (!inout) return fail(G16_ERR_BAD_ARGUMENT, "null buffer");
+    G16_NOT_BUSY();
     int rc = check_log(log_n);
     if (rc) return rc;
     G16_CUDA(cudaSetDevice(device));
@@ -304,6 +309,7 @@ struct Engine : IEngine {
 
   int witness_map_evals(uint32_t log_n, const uint64_t* a, const uint64_t* b, const uint64_t* c, uint64_t* h) override {
     if (!a || !b || !c || !h) return fail(G16_ERR_BAD_ARGUMENT, "null buffer");
+    G16_NOT_BUSY();
     int rc = check_log(log_n);
     if (rc) return rc;
     G16_CUDA(cudaSetDevice(device));
@@ -324,6 +330,7 @@ struct Engine : IEngine {
   int msm_host(WS& ws, const uint64_t* bases, const uint64_t* scalars, uint64_t n, uint64_t* out) {
     if (!out || (n && (!bases || !scalars))) return fail(G16_ERR_BAD_ARGUMENT, "null buffer");
     if (n >= (1ull << 27)) return fail(G16_ERR_BAD_ARGUMENT, "n too large");
+    G16_NOT_BUSY();
     G16_CUDA(cudaSetDevice(device));
     XYZZ<F> res = XYZZ<F>::inf();
     if (n) {
@@ -351,6 +358,7 @@ struct Engine : IEngine {
   // ---- circuit ----
   int circuit_load(uint32_t ni, uint32_t nc, uint32_t nw, const g16_csr* a, const g16_csr* b, const g16_csr* c) override {
     if (!a || !b || !c || ni == 0) return fail(G16_ERR_BAD_ARGUMENT, "bad circuit description");
+    G16_NOT_BUSY();
     uint64_t need = (uint64_t)nc + ni;
     int Ln = 0;
     while ((1ull << Ln) < need) Ln++;
@@ -413,6 +421,7 @@ struct Engine : IEngine {
   int pk_load(const g16_pk_desc* pk, uint32_t rk, uint32_t wd) override {
     if (!have_circuit) return fail(G16_ERR_BAD_ARGUMENT, "g16_circuit_load must precede g16_pk_load");
     if (!pk || wd == 0 || rk >= wd) return fail(G16_ERR_BAD_ARGUMENT, "bad pk / rank / world");
+    G16_NOT_BUSY();
     if (!pk->a_query || !pk->b_g1_query || !pk->b_g2_query || !pk->alpha_g1 || !pk->beta_g1 || !pk->delta_g1 || !pk->beta_g2 || !pk->delta_g2)
       return fail(G16_ERR_BAD_ARGUMENT, "null pk member");
     if (pk->a_len < 1 || pk->b_g1_len < 1 || pk->b_g2_len < 1) return fail(G16_ERR_MALFORMED_KEY, "a/b queries must hold at least the constant-one base");
@@ -453,6 +462,7 @@ struct Engine : IEngine {
             const uint64_t* tau_, const uint64_t* g1_, const uint64_t* g2_) override {
     if (!have_circuit) return fail(G16_ERR_BAD_ARGUMENT, "g16_circuit_load must precede g16_setup");
     if (!alpha_ || !beta_ || !gamma_ || !delta_ || !tau_ || !g1_ || !g2_) return fail(G16_ERR_BAD_ARGUMENT, "null argument");
+    G16_NOT_BUSY();
     G16_CUDA(cudaSetDevice(device));
     const Fr alpha = load_fr(alpha_), beta = load_fr(beta_), gamma = load_fr(gamma_), delta = load_fr(delta_), tau = load_fr(tau_);
     const A1 g1 = load_a1(g1_);

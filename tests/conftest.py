@@ -11,3 +11,19 @@ for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu under gpurun)")
+
+
+def _ensure_built():
+    """The shared libraries are build artefacts (git-ignored): build them on demand so that a fresh checkout can run the
+    CPU tier (ABI symbol check, oracle pinning) without a separate build step."""
+    import subprocess
+    lib = os.path.join(ROOT, "groth16_b200", "libg16b200.so")
+    orc = os.path.join(ROOT, "oracle", "liboracle.so")
+    jobs = str(max(1, min(16, os.cpu_count() or 1)))
+    if not os.path.exists(orc):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-j", jobs])
+    if not os.path.exists(lib):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "groth16_b200", "csrc"), "-j", jobs])
+
+
+_ensure_built()

@@ -404,6 +404,10 @@ struct Engine : IEngine {
     x.hi = rank + cnt;
     x.geom = with_k0(pick_geom(x.hi - x.lo), &x == &q[M_B2]);
   }
+  // sorted entries carry (copy * n + index) in 31 bits and offsets are 32-bit
+  bool geom_fits(const Query& x) const {
+    return (uint64_t)x.geom.copies * (x.hi - x.lo) < (1ull << 31) && x.geom.max_entries < (1ull << 32);
+  }
   template <class F>
   int upload_query(Query& x, const uint64_t* host_full, uint64_t skip_first) {
     using AT = Affine<F>;
@@ -436,6 +440,8 @@ struct Engine : IEngine {
     shard(q[M_A], std::min<uint64_t>(pk->a_len - 1, nz1));
     shard(q[M_B1], std::min<uint64_t>(pk->b_g1_len - 1, nz1));
     shard(q[M_B2], std::min<uint64_t>(pk->b_g2_len - 1, nz1));
+    for (int m = 0; m < 5; m++)
+      if (!geom_fits(q[m])) return fail(G16_ERR_BAD_ARGUMENT, "query too large for one GPU: shard it (world > 1) or raise G16_MSM_NE");
     int rc;
     if ((rc = upload_query<Fq>(q[M_H], pk->h_query, 0))) return rc;
     if ((rc = upload_query<Fq>(q[M_L], pk->l_query, 0))) return rc;

@@ -4,14 +4,16 @@
 // :74 (L query) and :262 (A, B-in-G1, B-in-G2 via calculate_coeff).  The group element returned is identical to
 // the reference's (EC addition is exactly associative/commutative), whatever the window size or summation order.
 //
-// Pipeline (all on one stream, no host synchronisation until the W window sums are read back):
-//   1. msm_digits<COUNT>   scalar -> W signed c-bit digits; histogram of (window, |digit|) keys (warp-aggregated atomics)
-//   2. msm_scan            exclusive prefix sum of the histogram -> bucket offsets
-//   3. msm_digits<SCATTER> counting-sort scatter: sorted (base index | sign) and key per entry
+// Resident bases come with precomputed multiples 2^(c*ne*j) * P (msm_precompute, copy-major), so that the W windows of a
+// scalar fall into only `ne` bucket sets (ne = 1 by default: one set of 2^(c-1) buckets for the whole MSM).
+// Pipeline (all on one stream, no host synchronisation until the leaf sums of the bucket reduction are read back):
+//   1. msm_digits<COUNT>   scalar -> W signed c-bit digits; histogram of (bucket set, |digit|) keys (warp-aggregated atomics)
+//   2. msm_scan_*          exclusive prefix sum of the histogram -> bucket offsets (three small launches)
+//   3. msm_digits<SCATTER> counting-sort scatter: sorted (copy * n + base index | sign) and key per entry
 //   4. msm_accum_l0        load-balanced segmented reduction: every thread owns K0 consecutive sorted entries,
 //                          mixed-adds them (XYZZ += affine, gathered from the resident base array), writes buckets
 //                          that are complete inside its chunk and emits <= 2 boundary partials
-//   5. msm_accum_ln        the same reduction over the partial list, level by level, until one thread remains
+//   5. msm_accum_ln/_tail  the same reduction over the partial list, level by level (empty levels return at once)
 //   6. msm_sum_strided     bucket reduction sum_b (b+1) B_b as two rounds of row / column block-tree sums
 //   host: weighted sums of the <= 64-point leaf arrays, Horner over effective windows; prover.rs semantics preserved.
 // Skewed scalar distributions (boolean witnesses, the reference's DummyCircuit whose witness is constant,
@@ -38,7 +40,7 @@ struct MsmGeom {
 };
 
 static constexpr int MSM_K0_MAX = 64;
-// Entries per thread so that the level-0 grid is at least ~2.5 waves of `resident_threads` (small MSMs, e.g. the per-rank
+// Entries per thread so that the level-0 grid is at least ~2 waves of `resident_threads` (small MSMs, e.g. the per-rank
 // shards of a multi-GPU proof, would otherwise run as a fraction of one wave: time = one 64-entry chunk regardless of size).
 inline int msm_pick_k0(uint64_t max_entries, uint64_t resident_threads, int k0_min) {
   int k0 = MSM_K0_MAX;

@@ -47,10 +47,11 @@ def parse():
                          "proof slots of a context (g16_prove_submit / g16_prove_wait).  Measured on B200: one proof already "
                          "keeps the multiplier pipes busy (5 MSM streams), so pipelining gains at most ~2%% and can lose when "
                          "two proofs' bulk kernels interleave (resident inputs) or an NCCL gather queues behind them")
-    ap.add_argument("--mode", default="shard", choices=["shard", "replicas"],
+    ap.add_argument("--mode", default="auto", choices=["auto", "shard", "replicas"],
                     help="N > 1: 'shard' splits every MSM of ONE proof over the GPUs (strong scaling, NCCL gather of partial "
-                         "points); 'replicas' lets every GPU prove its own proofs (weak scaling, no communication; "
-                         "BASELINE config 5)")
+                         "points: lowest latency); 'replicas' lets every GPU prove its own proofs (weak scaling, no "
+                         "communication: highest throughput; BASELINE config 5); 'auto' (default) measures the sharded proof "
+                         "first (reported under \"sharded\") and then reports the replica throughput as `value`")
     return ap.parse_args()
 
 
@@ -279,12 +280,12 @@ def run_cuda(a):
     G = GENERATORS[g.curve.name]
     t = time.time()
     pk = g.generate_parameters_with_qap(m, *TOXIC, G["g1"], G["g2"],
-                                        export=((world > 1 and a.mode == "shard") or not a.no_cpu_baseline))
-    replicas = world > 1 and a.mode == "replicas"
+                                        export=((world > 1 and a.mode != "replicas") or not a.no_cpu_baseline))
+    st = {"replicas": world > 1 and a.mode == "replicas"}
     sp = None
-    if world > 1 and not replicas:
+    if world > 1 and not st["replicas"]:
         from groth16_b200.dist import ShardedProver
-        sp = ShardedProver(g, pk, None, rank, world, dev)   # keep this rank's index range of every query
+        sp = ShardedProver(g, pk, None, rank, world, dev)   # keep this rank's round-robin share of every query
     t_setup = time.time() - t
     r = np.ascontiguousarray(cd.fr.enc1(123456789))
     s = np.ascontiguousarray(cd.fr.enc1(987654321))
@@ -294,7 +295,7 @@ def run_cuda(a):
     proof = np.zeros(8 * nq, dtype=np.uint64)
     def step(zptr, flags):
         """one proof; returns the proof limbs (every rank computes the same proof)"""
-        if world == 1 or replicas:
+        if world == 1 or st["replicas"]:
             g.prove_raw(r, s, zptr, flags, proof)
             return proof
         pf = sp.prove(r, s, zptr, flags)   # partial MSMs -> NCCL all_gather of 5 points per rank -> assemble
@@ -312,13 +313,13 @@ def run_cuda(a):
             return dev_ms, launches
 
         def submit(slot):
-            if world == 1 or replicas:
+            if world == 1 or st["replicas"]:
                 g.prove_submit_raw(slot, r, s, zptr, flags)
             else:
                 sp.submit(slot, r, zptr, flags)
 
         def finish(slot):
-            if world == 1 or replicas:
+            if world == 1 or st["replicas"]:
                 g.prove_wait_raw(slot, proof)
             else:
                 pf = sp.finish(slot, r, s)
@@ -362,10 +363,28 @@ def run_cuda(a):
         torch.cuda.synchronize()
         return 1e3 * (time.perf_counter() - t0) / reps
 
+    # ---- N > 1, auto: the sharded single proof first (NCCL path), then every GPU becomes a replica ----
+    sharded = None
+    if world > 1 and a.mode == "auto":
+        for _ in range(max(a.warmup, 3)):
+            step(z_dev.data_ptr(), _lib.ASSIGNMENT_ON_DEVICE)
+        shard_proof = step(z_dev.data_ptr(), _lib.ASSIGNMENT_ON_DEVICE).copy()
+        dt_s, dev_s, _, _ = timed(z_dev.data_ptr(), _lib.ASSIGNMENT_ON_DEVICE, a.steps)
+        step(z_pinned.data_ptr(), 0)
+        dt_s2, _, _, _ = timed(z_pinned.data_ptr(), 0, a.steps)
+        sharded = {"mode": f"msm-shard{world}: one proof per step, pair i of every MSM on rank i mod {world}, NCCL all_gather of 5 "
+                           "partial points per rank", "scaling": "strong", "value": a.steps / dt_s, "unit": "proofs/s",
+                   "latency_ms": 1e3 * dt_s / a.steps, "device_ms_per_step": statistics.mean(dev_s),
+                   "e2e_value": a.steps / dt_s2}
+        g.load_proving_key(pk, 0, 1)          # full key resident again: every rank proves on its own from here on
+        st["replicas"] = True
+    replicas = st["replicas"]
     # ---- warm-up, then the resident-input measurement (`value`) ----
     for _ in range(max(a.warmup, 3)):
         step(z_dev.data_ptr(), _lib.ASSIGNMENT_ON_DEVICE)
     first = step(z_dev.data_ptr(), _lib.ASSIGNMENT_ON_DEVICE).copy()
+    if sharded is not None:
+        assert np.array_equal(first, shard_proof), "sharded and single-GPU proofs differ"
     sampler = ClockSampler(local) if rank == 0 else None
     dt, dev_ms, launches, clocks = timed(z_dev.data_ptr(), _lib.ASSIGNMENT_ON_DEVICE, a.steps, sampler)
     units = world if replicas else 1          # proofs completed per step across the job
@@ -449,6 +468,8 @@ def run_cuda(a):
             "clocks": clocks,
             "setup_s": {"workload": t_work, "gpu_setup_and_key_residency": t_setup},
         }
+        if sharded:
+            line["sharded"] = sharded
         if roof:
             line["roofline"] = roof
             line["kernels"] = kern

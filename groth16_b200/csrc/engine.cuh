@@ -135,6 +135,9 @@ struct Engine : IEngine {
   int sm_count = 148;
   MsmGeom with_k0(MsmGeom g, bool g2) const {
     g.k0 = msm_pick_k0(g.max_entries, (uint64_t)sm_count * 128 * (g2 ? 2 : 3), g2 ? 16 : 8);
+    // G2 additions are ~3x longer: 32 entries per thread (twice the thread count) shortens the last partial wave (-13 %)
+    if (g2 && g.k0 > 32) g.k0 = 32;
+    if (const char* v = getenv(g2 ? "G16_ACC_K0_G2" : "G16_ACC_K0_G1")) { const int k = atoi(v); if (k >= 4 && k <= 1024) g.k0 = k; }
     return g;
   }
   template <class F>

@@ -624,7 +624,10 @@ cudaError_t msm_enqueue(cudaStream_t st, MsmWorkspace<F>& ws, const MsmGeom& g, 
   uint32_t* kk[2] = {ws.pk0.template as<uint32_t>(), ws.pk1.template as<uint32_t>()};
   XYZZ<F>* pp[2] = {ws.pp0.template as<XYZZ<F>>(), ws.pp1.template as<XYZZ<F>>()};
   if (ev_acc0) cudaEventRecord(ev_acc0, st);
-  msm_accum_l0<F><<<(unsigned)((T0 + 127) / 128), 128, 0, st>>>(d_bases, sidx, skey, offsets + g.nkeys, T0, (uint32_t)g.k0, buckets, kk[0], pp[0], pending);
+  {
+    static const unsigned tpb = [] { const char* e = getenv("G16_ACC_BLOCK"); int v = e ? atoi(e) : 128; return (unsigned)((v == 32 || v == 64) ? v : 128); }();
+    msm_accum_l0<F><<<(unsigned)((T0 + tpb - 1) / tpb), tpb, 0, st>>>(d_bases, sidx, skey, offsets + g.nkeys, T0, (uint32_t)g.k0, buckets, kk[0], pp[0], pending);
+  }
   if (ev_acc1) cudaEventRecord(ev_acc1, st);
   nl += 1;
   // levels >= 1: ping-pong between the two partial buffers, then one fused tail; empty levels return immediately

@@ -375,3 +375,50 @@ def test_pipelined_proofs_equal_sequential():
         assert np.array_equal(a_, b_)
     with pytest.raises(ValueError):   # waiting on an idle slot is an error, not a hang
         g.prove_wait_raw(0, outs[0])
+
+
+@pytest.mark.parametrize("curve", ["bn254", "bls12_381"])
+def test_edge_circuits(curve):
+    """Edge shapes around the witness map and the MSM entry counts, each against the big-int oracle:
+    (a) no public inputs (instance = [One]); (b) num_constraints + num_instance exactly 2^k and 2^k + 1 (domain doubles);
+    (c) an all-zero witness (every MSM over the witness sorts ZERO entries: empty partial lists, empty buckets);
+    (d) a single constraint."""
+    c = P.CURVES[curve]
+    g = engine(curve)
+    cd = g.codec
+    rng = P.Rng(61)
+    r = c.r
+
+    def chain(n_constraints, n_inputs, zero=False):
+        # x_{i+1} = (x_i + k_i) * x_i ; the last n_inputs products are public
+        ninst = 1 + n_inputs
+        vals = [0 if zero else rng.fr(r)]
+        cols = [ninst]
+        A, B, C, inst, wit = [], [], [], [], list(vals)
+        for i in range(n_constraints):
+            k = 0 if zero else rng.fr(r)
+            v = (vals[-1] + k) * vals[-1] % r
+            if i >= n_constraints - n_inputs:
+                col = 1 + len(inst); inst.append(v)
+            else:
+                col = ninst + len(wit); wit.append(v)
+            A.append([(1, cols[-1])] + ([(k, 0)] if k else [])); B.append([(1, cols[-1])]); C.append([(1, col)])
+            cols.append(col); vals.append(v)
+        return P.R1CS(c, ninst, len(wit), A, B, C, [1] + inst + wit)
+
+    cases = [chain(5, 0), chain(6, 1), chain(7, 1), chain(1, 1), chain(9, 2, zero=True), chain(14, 1), chain(15, 1)]
+    for cs in cases:
+        assert cs.is_satisfied()
+        tw = toxic(c, 70 + cs.num_constraints)
+        opk = P.generate_parameters(cs, *tw)
+        g.load_matrices(matrices_from_r1cs(cs))
+        g.load_proving_key(pk_to_abi(opk))
+        z = cd.fr.enc(cs.assignment)
+        h = cd.fr.dec(g.witness_map_from_matrices(None, cs.num_instance, cs.num_constraints, z))
+        assert h == P.witness_map(cs)
+        r_, s_ = rng.fr(r), rng.fr(r)
+        pf = proof_from_abi(curve, g.create_proof_with_reduction_and_matrices(None, r_, s_, None, cs.num_instance,
+                                                                              cs.num_constraints, z))
+        want = P.create_proof(opk, cs, r_, s_)
+        assert (pf.a, pf.b, pf.c) == (want.a, want.b, want.c)
+    assert P.verify_proof(opk.vk, c, pf, cs.assignment[1:cs.num_instance])

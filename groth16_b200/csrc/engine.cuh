@@ -138,6 +138,11 @@ struct Engine : IEngine {
     // G2 additions are ~3x longer: 32 entries per thread (twice the thread count) shortens the last partial wave (-13 %)
     if (g2 && g.k0 > 32) g.k0 = 32;
     if (const char* v = getenv(g2 ? "G16_ACC_K0_G2" : "G16_ACC_K0_G1")) { const int k = atoi(v); if (k >= 4 && k <= 1024) g.k0 = k; }
+    // experimental batched-affine pre-reduction (msm_ba.cuh): rounds for G1 / G2 MSMs with at least 2^18 entries
+    if (const char* v = getenv(g2 ? "G16_MSM_BA_G2" : "G16_MSM_BA")) {
+      const int r = atoi(v);
+      if (r > 0 && r <= MSM_BA_MAX_ROUNDS && g.max_entries >= (1u << 18)) g.ba = r;
+    }
     return g;
   }
   template <class F>

@@ -37,6 +37,7 @@ struct MsmGeom {
   uint32_t nkeys;    // ne * B
   uint64_t max_entries;  // n * W
   int k0;            // sorted entries per thread in the level-0 accumulation (64 for large MSMs, less to fill the GPU)
+  int ba;            // batched-affine pre-reduction rounds before the accumulation (msm_ba.cuh); 0 = none
 };
 
 static constexpr int MSM_K0_MAX = 64;
@@ -68,6 +69,7 @@ inline MsmGeom msm_geom(uint64_t n, int scalar_bits, int c_override = 0, int ne_
   g.nkeys = (uint32_t)g.ne * g.B;
   g.max_entries = (uint64_t)n * g.W;
   g.k0 = MSM_K0_MAX;
+  g.ba = 0;
   return g;
 }
 
@@ -198,6 +200,10 @@ static __global__ void __launch_bounds__(1024) msm_scan_fix(uint32_t* offsets, u
       cursors[base + k] = o;
     }
 }
+
+}  // namespace g16
+#include "msm_ba.cuh"   // optional batched-affine pre-reduction (uses block_exclusive_scan_1024)
+namespace g16 {
 
 // ------------------------------------------------------------------------------------------------
 // 4/5. load-balanced segmented bucket accumulation
@@ -536,20 +542,65 @@ struct DevBuf {
 static constexpr int MSM_KF = 4;       // partial slots per thread, levels >= 1
 static constexpr int MSM_TAIL_S = 2048;  // partial-list length at which the remaining levels fuse into one block
 
+// Host-side plan of the batched-affine rounds of one MSM (msm_ba.cuh): upper bounds of the list lengths (the true
+// lengths live on the device), outputs per thread of every round and the entries per thread of the accumulation
+// that finishes the last list.
+static constexpr int MSM_BA_MAX_ROUNDS = 6;
+static constexpr uint32_t MSM_BA_G = 64;   // thread products per combine lane = per field inversion
+struct MsmBaPlan {
+  int R = 0;
+  uint64_t len[MSM_BA_MAX_ROUNDS + 1] = {0};
+  uint32_t m[MSM_BA_MAX_ROUNDS] = {0};
+  uint64_t threads_max = 0;
+  int k0_final = 0;
+  void make(const MsmGeom& g) {
+    R = g.ba < 0 ? 0 : (g.ba > MSM_BA_MAX_ROUNDS ? MSM_BA_MAX_ROUNDS : g.ba);
+    len[0] = g.max_entries;
+    threads_max = 0;
+    for (int r = 0; r < R; r++) {
+      len[r + 1] = ba_next_max(len[r], g.nkeys);
+      uint32_t mm = 32;
+      while (mm > 4 && len[r + 1] / mm < 200000) mm >>= 1;
+      m[r] = mm;
+      const uint64_t T = ba_threads(len[r + 1], mm);
+      if (T > threads_max) threads_max = T;
+    }
+    k0_final = g.k0 >> R;
+    if (k0_final < 8) k0_final = g.k0 < 8 ? g.k0 : 8;
+  }
+  // threads of the level-0 accumulation
+  uint64_t l0_threads(const MsmGeom& g) const {
+    return R > 0 ? (len[R] + k0_final - 1) / k0_final : (g.max_entries + g.k0 - 1) / g.k0;
+  }
+};
+
 template <class F>
 struct MsmWorkspace {
   DevBuf counters, offsets, blocktot, sidx, skey, buckets, pk0, pp0, pk1, pp1, pending, red_inner, red_leaf;
+  DevBuf ba_off, ba_pre, ba_key, ba_ident, ba_prod, ba_pre2, ba_l0, ba_l1;
+  MsmBaPlan bap;
   MsmRedPlan plan;
   int plan_m = -1, plan_ne = 0;
   XYZZ<F>* h_leaf = nullptr;  // pinned host copy of the leaf arrays: [node][window][element]
   size_t h_cap = 0;
   cudaError_t prepare(const MsmGeom& g) {
     cudaError_t e;
-    const uint64_t T0 = (g.max_entries + g.k0 - 1) / g.k0;
+    bap.make(g);
+    const uint64_t T0 = bap.l0_threads(g);
     const uint64_t S1 = 2 * T0;
     const uint64_t T1 = msm_level_threads(S1, MSM_KF);
     const uint64_t S2 = 2 * T1;
 #define G16_TRY(x) if ((e = (x)) != cudaSuccess) return e
+    if (bap.R > 0) {
+      G16_TRY(ba_off.reserve((size_t)(bap.R + 1) * (g.nkeys + 1) * 4));
+      G16_TRY(ba_pre.reserve(bap.len[1] * sizeof(F) + 16));
+      G16_TRY(ba_key.reserve(bap.len[1] * 4 + 16));
+      G16_TRY(ba_ident.reserve(bap.len[1] * 4 + 16));
+      G16_TRY(ba_prod.reserve(bap.threads_max * sizeof(F) + 16));
+      G16_TRY(ba_pre2.reserve(bap.threads_max * sizeof(F) + 16));
+      G16_TRY(ba_l0.reserve(bap.len[1] * sizeof(Affine<F>) + 16));
+      if (bap.R > 1) G16_TRY(ba_l1.reserve(bap.len[2] * sizeof(Affine<F>) + 16));
+    }
     G16_TRY(counters.reserve((size_t)(g.nkeys + 1) * 4));
     G16_TRY(offsets.reserve((size_t)(g.nkeys + 1) * 4));
     G16_TRY(blocktot.reserve((size_t)((g.nkeys + SCAN_BLOCK - 1) / SCAN_BLOCK + 1) * 4));
@@ -581,6 +632,8 @@ struct MsmWorkspace {
   void release() {
     counters.release(); offsets.release(); blocktot.release(); sidx.release(); skey.release(); buckets.release();
     pk0.release(); pp0.release(); pk1.release(); pp1.release(); pending.release(); red_inner.release(); red_leaf.release();
+    ba_off.release(); ba_pre.release(); ba_key.release(); ba_ident.release(); ba_prod.release(); ba_pre2.release();
+    ba_l0.release(); ba_l1.release();
     if (h_leaf) cudaFreeHost(h_leaf);
     h_leaf = nullptr;
     h_cap = 0;
@@ -619,14 +672,50 @@ cudaError_t msm_enqueue(cudaStream_t st, MsmWorkspace<F>& ws, const MsmGeom& g, 
   msm_scan_fix<<<sb, 1024, 0, st>>>(offsets, g.nkeys, blocktot, counters);
   msm_digits<FrF, true><<<nb, 256, 0, st>>>(d_scalars, scalar_stride, scalars_mont ? 1 : 0, d_skip, g, counters, sidx, skey);
   nl += 5;
+  // optional batched-affine rounds: the sorted entries shrink to a list of partial bucket sums (msm_ba.cuh)
+  const MsmBaPlan& bp = ws.bap;
+  const Affine<F>* acc_bases = d_bases;
+  const uint32_t *acc_sidx = sidx, *acc_skey = skey, *acc_total = offsets + g.nkeys;
+  if (ev_acc0) cudaEventRecord(ev_acc0, st);
+  if (bp.R > 0) {
+    uint32_t* ba_off = ws.ba_off.template as<uint32_t>();
+    Affine<F>* lists[2] = {ws.ba_l0.template as<Affine<F>>(), ws.ba_l1.template as<Affine<F>>()};
+    ba_offsets_kernel<<<1, 1024, 0, st>>>(offsets, g.nkeys, bp.R, ba_off);
+    nl += 1;
+    for (int r = 0; r < bp.R; r++) {
+      BaRound<F> a;
+      a.in = r == 0 ? d_bases : lists[(r - 1) & 1];
+      a.sidx = r == 0 ? sidx : nullptr;
+      a.off_in = ba_off + (size_t)r * (g.nkeys + 1);
+      a.off_out = ba_off + (size_t)(r + 1) * (g.nkeys + 1);
+      a.nkeys = g.nkeys;
+      a.m = bp.m[r];
+      a.G = MSM_BA_G;
+      a.pre = ws.ba_pre.template as<F>();
+      a.key = ws.ba_key.template as<uint32_t>();
+      a.ident = ws.ba_ident.template as<uint32_t>();
+      a.prod = ws.ba_prod.template as<F>();
+      a.pre2 = ws.ba_pre2.template as<F>();
+      a.out = lists[r & 1];
+      const uint64_t T = ba_threads(bp.len[r + 1], a.m), lanes = (T + a.G - 1) / a.G;
+      ba_forward_kernel<F><<<(unsigned)((T + 127) / 128), 128, 0, st>>>(a);
+      ba_combine_kernel<F><<<(unsigned)((lanes + 31) / 32), 32, 0, st>>>(a);
+      ba_backward_kernel<F><<<(unsigned)((T + 127) / 128), 128, 0, st>>>(a);
+      nl += 3;
+    }
+    acc_bases = lists[(bp.R - 1) & 1];
+    acc_sidx = ws.ba_ident.template as<uint32_t>();
+    acc_skey = ws.ba_key.template as<uint32_t>();
+    acc_total = ba_off + (size_t)bp.R * (g.nkeys + 1) + g.nkeys;
+  }
   // level 0
-  const uint64_t T0 = (g.max_entries + g.k0 - 1) / g.k0;
+  const uint64_t T0 = bp.l0_threads(g);
+  const uint32_t K0 = bp.R > 0 ? (uint32_t)bp.k0_final : (uint32_t)g.k0;
   uint32_t* kk[2] = {ws.pk0.template as<uint32_t>(), ws.pk1.template as<uint32_t>()};
   XYZZ<F>* pp[2] = {ws.pp0.template as<XYZZ<F>>(), ws.pp1.template as<XYZZ<F>>()};
-  if (ev_acc0) cudaEventRecord(ev_acc0, st);
   {
     static const unsigned tpb = [] { const char* e = getenv("G16_ACC_BLOCK"); int v = e ? atoi(e) : 128; return (unsigned)((v == 32 || v == 64) ? v : 128); }();
-    msm_accum_l0<F><<<(unsigned)((T0 + tpb - 1) / tpb), tpb, 0, st>>>(d_bases, sidx, skey, offsets + g.nkeys, T0, (uint32_t)g.k0, buckets, kk[0], pp[0], pending);
+    msm_accum_l0<F><<<(unsigned)((T0 + tpb - 1) / tpb), tpb, 0, st>>>(acc_bases, acc_sidx, acc_skey, acc_total, T0, K0, buckets, kk[0], pp[0], pending);
   }
   if (ev_acc1) cudaEventRecord(ev_acc1, st);
   nl += 1;

@@ -278,9 +278,7 @@ def test_prove_synthetic_2p14(curve):
     assert np.array_equal(h, orc.witness_map(P.CURVES[curve].cid, m, z, threads=8))
 
 
-def test_msm_skewed_scalars_large():
-    """2^15-point G1 MSM whose scalars are 50 % in {0,1}, 25 % < 2^32, 25 % uniform (SURVEY.md section 8d 'realistic mix'):
-    giant buckets exercise every level of the segmented reduction.  Checked against the CPU oracle."""
+def _skewed_msm_check():
     import orc
     curve = "bls12_381"
     c = P.CURVES[curve]
@@ -292,6 +290,7 @@ def test_msm_skewed_scalars_large():
     ks = rs.randint(0, 1 << 62, size=(n, 4), dtype=np.int64).astype(np.uint64)
     ks[:, 3] &= np.uint64((1 << 58) - 1)
     bases = orc.batch_mul_g1(c.cid, cd.nq, cd.enc_g1([GENERATORS[curve]["g1"]])[0], ks, threads=8)
+    bases[5::97] = bases[4::97][:len(bases[5::97])]   # repeated bases: equal points meet inside a bucket
     sc = rs.randint(0, 1 << 62, size=(n, 4), dtype=np.int64).astype(np.uint64)
     sc[:, 3] &= np.uint64((1 << 58) - 1)
     kind = rs.randint(0, 4, size=n)
@@ -300,6 +299,41 @@ def test_msm_skewed_scalars_large():
     sc[kind == 2, 1:] = 0
     sc[kind == 2, 0] &= np.uint64(0xFFFFFFFF)
     assert np.array_equal(g.msm_g1(bases, sc), orc.msm_g1(c.cid, cd.nq, bases, sc, threads=8))
+
+
+def test_msm_skewed_scalars_large():
+    """2^15-point G1 MSM whose scalars are 50 % in {0,1}, 25 % < 2^32, 25 % uniform (SURVEY.md section 8d 'realistic mix'),
+    some bases repeated: giant buckets exercise every level of the segmented reduction.  Checked against the CPU oracle."""
+    _skewed_msm_check()
+
+
+@pytest.mark.parametrize("rounds", [1, 3])
+def test_batched_affine_rounds(monkeypatch, rounds):
+    """The experimental batched-affine pre-reduction (csrc/msm_ba.cuh, G16_MSM_BA / G16_MSM_BA_G2 = rounds) must not
+    change a single bit: skewed G1 MSM with repeated bases, a 2^14-point G2 MSM, and full proofs (synthetic 2^14, and the
+    degenerate DummyCircuit where every scalar is equal) against the CPU oracle."""
+    import orc
+    from groth16_b200.params import GENERATORS
+    from groth16_b200.workload import dummy_r1cs, synthetic_r1cs
+    monkeypatch.setenv("G16_MSM_BA", str(rounds))
+    monkeypatch.setenv("G16_MSM_BA_G2", str(rounds))
+    _skewed_msm_check()
+    curve = "bn254"
+    c = P.CURVES[curve]
+    g = engine(curve)
+    cd = g.codec
+    n = 1 << 14
+    rs = np.random.RandomState(11)
+    ks = rs.randint(0, 1 << 62, size=(n, 4), dtype=np.int64).astype(np.uint64)
+    ks[:, 3] &= np.uint64((1 << 58) - 1)
+    bases = orc.batch_mul_g2(c.cid, cd.nq, cd.enc_g2([GENERATORS[curve]["g2"]])[0], ks, threads=8)
+    sc = rs.randint(0, 1 << 62, size=(n, 4), dtype=np.int64).astype(np.uint64)
+    sc[:, 3] &= np.uint64((1 << 58) - 1)
+    assert np.array_equal(g.msm_g2(bases, sc), orc.msm_g2(c.cid, cd.nq, bases, sc, threads=8))
+    m, z, _ = synthetic_r1cs("bls12_381", 14, seed=9)
+    _oracle_vs_gpu("bls12_381", m, z)
+    m, z, _ = dummy_r1cs("bls12_377", (1 << 14) - 100, (1 << 14) - 100)
+    _oracle_vs_gpu("bls12_377", m, z)
 
 
 def test_api_error_paths():

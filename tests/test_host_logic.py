@@ -144,3 +144,18 @@ def test_msm_reduction_plan_host(tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "18 cases, 0 mismatches" in out.stdout
+
+
+def test_batched_affine_rounds_host(tmp_path):
+    """msm_ba.cuh: the per-thread bodies of the batched-affine rounds (forward products, one inversion per combine lane,
+    backward additions; tangent / opposite / identity cases; ragged buckets) executed on the CPU for G1 and both Fq2
+    towers: every bucket of the reduced list sums to the plain XYZZ sum of its entries, and MsmBaPlan's bounds hold."""
+    import shutil
+    if shutil.which("nvcc") is None:
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "ba_check")
+    subprocess.check_call(["nvcc", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-O1", "-o", exe,
+                           os.path.join(ROOT, "tests", "host", "ba_check.cu")])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "12 cases, 0 mismatches" in out.stdout

@@ -200,6 +200,22 @@ class Groth16:
         _check(self._lib.g16_msm_g2(self._ctx, _ptr(bases), _ptr(scalars), n, _ptr(out)))
         return out
 
+    def prepare_inputs(self, vk: VerifyingKey, public_inputs) -> np.ndarray:
+        """Groth16::prepare_inputs (verifier.rs:25-39): gamma_abc_g1[0] + sum_i x_i * gamma_abc_g1[i + 1], computed as ONE G1
+        MSM with scalars (1, x_0, x_1, ...).  `public_inputs`: Python ints, or an (l, 4) array of Montgomery Fr limbs (ark's
+        memory image).  Returns the projective point in msm_g1's encoding.  A length mismatch is
+        SynthesisError::MalformedVerifyingKey (verifier.rs:30)."""
+        if vk.gamma_abc_g1 is None:
+            raise MalformedKey("verifying key has no gamma_abc_g1")
+        abc = np.ascontiguousarray(vk.gamma_abc_g1, dtype=np.uint64).reshape(-1, 2 * self.nq)
+        if isinstance(public_inputs, np.ndarray):
+            xs = self.codec.fr.dec(np.ascontiguousarray(public_inputs, dtype=np.uint64).reshape(-1, 4))
+        else:
+            xs = [int(x) % self.curve.r for x in public_inputs]
+        if len(xs) + 1 != abc.shape[0]:
+            raise MalformedKey("public input count does not match the verifying key")
+        return self.msm_g1(abc, self.codec.fr.bigint([1] + xs))
+
     # ---- resident state ----
     def load_matrices(self, m: ConstraintMatrices):
         def csr(t):

@@ -336,6 +336,13 @@ def test_batched_affine_rounds(monkeypatch, rounds):
     _oracle_vs_gpu("bls12_377", m, z)
 
 
+@pytest.mark.parametrize("curve", ALL_CURVES)
+def test_prepare_inputs(curve):
+    """verifier.rs:25-39 as one G1 MSM on the GPU (see util.check_prepare_inputs)."""
+    from util import check_prepare_inputs
+    check_prepare_inputs(engine(curve), curve)
+
+
 def test_api_error_paths():
     """Status codes instead of panics across the ABI (Cargo.toml:61 panic='abort' rationale): wrong order of calls, bad
     indices, sharded key used with the single-GPU entry point, domain larger than the field's two-adicity."""

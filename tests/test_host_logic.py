@@ -159,3 +159,25 @@ def test_batched_affine_rounds_host(tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "12 cases, 0 mismatches" in out.stdout
+
+
+def test_prepare_inputs_host_logic():
+    """api.Groth16.prepare_inputs (verifier.rs:25-39) with the MSM call replaced by the CPU oracle: scalar conversion
+    (ints and Montgomery limbs -> BigInt), the leading 1 for gamma_abc_g1[0], and the MalformedVerifyingKey check."""
+    import orc
+    import pyref as P
+    from groth16_b200 import CurveCodec, Groth16, get_curve
+    from util import check_prepare_inputs
+
+    class CpuMsm(Groth16):
+        def __init__(self, name):
+            self.curve = get_curve(name)
+            self.codec = CurveCodec(self.curve)
+            self.nq = self.codec.nq
+            self._cid = P.CURVES[name].cid
+
+        def msm_g1(self, bases, scalars):
+            return orc.msm_g1(self._cid, self.nq, bases, scalars, threads=2)
+
+    for name in ("bn254", "bls12_381"):
+        check_prepare_inputs(CpuMsm(name), name)

@@ -36,3 +36,26 @@ def proof_from_abi(curve_name: str, pf) -> "P.Proof":
 def toxic(curve, seed):
     rng = P.Rng(seed)
     return [rng.fr(curve.r) for _ in range(5)]
+
+
+def check_prepare_inputs(g, curve_name: str):
+    """Groth16::prepare_inputs (verifier.rs:25-39) through `g` against the group law of the big-int oracle; both input
+    forms (ints, Montgomery limbs); MalformedVerifyingKey on a length mismatch (verifier.rs:30)."""
+    import pytest
+    from groth16_b200 import MalformedKey
+    c = P.CURVES[curve_name]
+    cx = P.ctx(c)
+    cd = CurveCodec(get_curve(curve_name))
+    rng = P.Rng(77)
+    pts = [cx.G1.mul(cx.g1_gen(), rng.fr(c.r)) for _ in range(5)]
+    xs = [0, 1, c.r - 1, rng.fr(c.r)]
+    vk = VerifyingKey(None, None, None, None, cd.enc_g1(pts))
+    want = pts[0]
+    for x, b in zip(xs, pts[1:]):
+        want = cx.G1.add(want, cx.G1.mul(b, x))
+    assert cd.dec_proj_g1(g.prepare_inputs(vk, xs)) == want
+    assert cd.dec_proj_g1(g.prepare_inputs(vk, cd.fr.enc(xs))) == want
+    with pytest.raises(MalformedKey):
+        g.prepare_inputs(vk, xs[:-1])
+    with pytest.raises(MalformedKey):
+        g.prepare_inputs(VerifyingKey(None, None, None, None, None), xs)

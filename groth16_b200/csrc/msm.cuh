@@ -680,6 +680,7 @@ cudaError_t msm_enqueue(cudaStream_t st, MsmWorkspace<F>& ws, const MsmGeom& g, 
   if (bp.R > 0) {
     uint32_t* ba_off = ws.ba_off.template as<uint32_t>();
     Affine<F>* lists[2] = {ws.ba_l0.template as<Affine<F>>(), ws.ba_l1.template as<Affine<F>>()};
+    static const uint32_t ba_gcd = [] { const char* e = getenv("G16_BA_INV_GCD"); return (uint32_t)(e && atoi(e) > 0); }();
     ba_offsets_kernel<<<1, 1024, 0, st>>>(offsets, g.nkeys, bp.R, ba_off);
     nl += 1;
     for (int r = 0; r < bp.R; r++) {
@@ -691,6 +692,7 @@ cudaError_t msm_enqueue(cudaStream_t st, MsmWorkspace<F>& ws, const MsmGeom& g, 
       a.nkeys = g.nkeys;
       a.m = bp.m[r];
       a.G = MSM_BA_G;
+      a.inv_gcd = ba_gcd;
       a.pre = ws.ba_pre.template as<F>();
       a.key = ws.ba_key.template as<uint32_t>();
       a.ident = ws.ba_ident.template as<uint32_t>();

@@ -15,13 +15,15 @@
 //             thread product -> prod[t]
 //   combine : lane g owns G thread products: Montgomery's trick over them, ONE inversion per lane, prod[t] <- prod[t]^-1
 //   backward: thread t walks its outputs in reverse, recovers 1/d_j, finishes the additions, writes list_{r+1}
-// = 6 multiplications per addition + (3 + inv/G)/m for the combine (inv ~ 570, Fermat).
+// = 6 multiplications per addition + (3 + inv/G)/m for the combine (inv ~ 570 multiplications with Fermat; the
+// safegcd inversion of fp_inv.cuh, ~10x fewer instructions, is selectable: G16_BA_INV_GCD=1, not yet run on a GPU).
 //
 // Every per-thread body below is __host__ __device__ and free of warp intrinsics, so tests/host/ba_check.cu runs
 // the same code on the CPU against plain XYZZ sums (exceptional cases included: equal points, opposite points,
 // identities in the lists).
 #pragma once
 #include "ec.cuh"
+#include "fp_inv.cuh"
 
 namespace g16 {
 
@@ -34,6 +36,7 @@ struct BaRound {
   uint32_t nkeys;
   uint32_t m;                // outputs per thread
   uint32_t G;                // thread products per combine lane
+  uint32_t inv_gcd;          // combine: 1 = safegcd inversion (fp_inv.cuh), 0 = Fermat
   F* pre;                    // [outputs]  running product of the thread before output j
   uint32_t* key;             // [outputs]  bucket of output j
   uint32_t* ident;           // [outputs]  j  (the index list msm_accum_l0 wants for the final list)
@@ -131,6 +134,17 @@ G16_HD void ba_forward(const BaRound<F>& a, uint64_t t) {
   a.prod[t] = run;
 }
 
+// the one inversion of a combine lane
+template <class P>
+G16_HD Fp<P> ba_inv(const Fp<P>& a, bool gcd) { return gcd ? fp_inv_safegcd<P>(a) : Fp<P>::inv(a); }
+template <class P, int NR>
+G16_HD Fp2<P, NR> ba_inv(const Fp2<P, NR>& a, bool gcd) {
+  using B = Fp<P>;
+  const B n = B::add(B::sqr(a.c0), Fp2<P, NR>::mul_nr(B::sqr(a.c1)));
+  const B ni = ba_inv(n, gcd);
+  return {B::mul(a.c0, ni), B::neg(B::mul(a.c1, ni))};
+}
+
 template <class F>
 G16_HD void ba_combine(const BaRound<F>& a, uint64_t g) {
   const uint32_t M = a.off_out[a.nkeys];
@@ -143,7 +157,7 @@ G16_HD void ba_combine(const BaRound<F>& a, uint64_t g) {
     a.pre2[k] = acc;
     acc = F::mul(acc, a.prod[k]);
   }
-  F inv = F::inv(acc);   // never zero: every factor is x2 - x1 != 0, 2 y1 != 0 or one
+  F inv = ba_inv(acc, a.inv_gcd != 0);   // never zero: every factor is x2 - x1 != 0, 2 y1 != 0 or one
   for (uint64_t k = hi; k-- > lo;) {
     const F pk = a.prod[k];
     a.prod[k] = F::mul(inv, a.pre2[k]);

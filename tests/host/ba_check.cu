@@ -20,7 +20,7 @@ static bool same_pt(const XYZZ<F>& a, const XYZZ<F>& b) {
 }
 
 template <class F>
-static int run_case(const Affine<F>& G, uint32_t nkeys, uint32_t nbase, uint32_t avg, int R, uint32_t m, uint32_t Gc, const char* name) {
+static int run_case(const Affine<F>& G, uint32_t nkeys, uint32_t nbase, uint32_t avg, int R, uint32_t m, uint32_t Gc, const char* name, uint32_t gcd = 0) {
   int bad = 0;
   // base table: k * G, a few identities
   std::vector<Affine<F>> bases(nbase);
@@ -78,7 +78,7 @@ static int run_case(const Affine<F>& G, uint32_t nkeys, uint32_t nbase, uint32_t
     a.sidx = r == 0 ? sidx.data() : nullptr;
     a.off_in = &off_all[(size_t)r * (nkeys + 1)];
     a.off_out = &off_all[(size_t)(r + 1) * (nkeys + 1)];
-    a.nkeys = nkeys; a.m = m; a.G = Gc;
+    a.nkeys = nkeys; a.m = m; a.G = Gc; a.inv_gcd = gcd;
     a.pre = pre.data(); a.key = key.data(); a.ident = ident.data(); a.prod = prod.data(); a.pre2 = pre2.data();
     a.out = lists[r & 1].data();
     const uint64_t Tmax = ba_threads(bp.len[r + 1], m) + 3;   // over-launch like the kernels do
@@ -115,6 +115,7 @@ int main() {
       bad += run_case<F>(G, 5, 3, 40, R, 8, 64, "bn254-g1-dense"); cases++;
     }
     bad += run_case<F>(G, 1, 9, 100, 6, 32, 64, "bn254-g1-onebucket"); cases++;
+    bad += run_case<F>(G, 37, 50, 12, 3, 4, 3, "bn254-g1-safegcd", 1); cases++;
   }
   {
     using B = Fp<BLS381_FqP>;
@@ -123,6 +124,7 @@ int main() {
     const Affine<F> G{{small(3), small(5)}, {small(7), small(11)}};
     bad += run_case<F>(G, 19, 20, 6, 2, 4, 5, "bls381-g2"); cases++;
     bad += run_case<F>(G, 3, 4, 20, 3, 16, 64, "bls381-g2-dense"); cases++;
+    bad += run_case<F>(G, 19, 20, 6, 2, 4, 5, "bls381-g2-safegcd", 1); cases++;
   }
   {
     using B = Fp<BLS377_FqP>;

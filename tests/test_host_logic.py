@@ -158,7 +158,7 @@ def test_batched_affine_rounds_host(tmp_path):
                            os.path.join(ROOT, "tests", "host", "ba_check.cu")])
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert "12 cases, 0 mismatches" in out.stdout
+    assert "14 cases, 0 mismatches" in out.stdout
 
 
 def test_prepare_inputs_host_logic():
@@ -181,3 +181,13 @@ def test_prepare_inputs_host_logic():
 
     for name in ("bn254", "bls12_381"):
         check_prepare_inputs(CpuMsm(name), name)
+
+
+def test_safegcd_inversion_host(tmp_path):
+    """fp_inv.cuh: Bernstein-Yang division-step inversion (signed 30-bit limbs) == Fermat inversion for all six fields:
+    random elements, every 2^k and 2^k - 1, p - 1, p - 2, (p +- 1)/2, zero; x * inv(x) == 1."""
+    exe = str(tmp_path / "inv_check")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-x", "c++", os.path.join(ROOT, "tests", "host", "inv_check.cpp"), "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "total 0 mismatches" in out.stdout

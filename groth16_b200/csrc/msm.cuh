@@ -559,7 +559,8 @@ struct MsmBaPlan {
     threads_max = 0;
     for (int r = 0; r < R; r++) {
       len[r + 1] = ba_next_max(len[r], g.nkeys);
-      uint32_t mm = 32;
+      static const uint32_t m_max = [] { const char* e = getenv("G16_BA_M"); const int v = e ? atoi(e) : 32; return (uint32_t)((v >= 1 && v <= 256) ? v : 32); }();
+      uint32_t mm = m_max;
       while (mm > 4 && len[r + 1] / mm < 200000) mm >>= 1;
       m[r] = mm;
       const uint64_t T = ba_threads(len[r + 1], mm);
@@ -680,6 +681,7 @@ cudaError_t msm_enqueue(cudaStream_t st, MsmWorkspace<F>& ws, const MsmGeom& g, 
   if (bp.R > 0) {
     uint32_t* ba_off = ws.ba_off.template as<uint32_t>();
     Affine<F>* lists[2] = {ws.ba_l0.template as<Affine<F>>(), ws.ba_l1.template as<Affine<F>>()};
+    static const uint32_t ba_G = [] { const char* e = getenv("G16_BA_G"); const int v = e ? atoi(e) : (int)MSM_BA_G; return (uint32_t)((v >= 1 && v <= 4096) ? v : (int)MSM_BA_G); }();
     static const uint32_t ba_gcd = [] { const char* e = getenv("G16_BA_INV_GCD"); return (uint32_t)(e && atoi(e) > 0); }();
     ba_offsets_kernel<<<1, 1024, 0, st>>>(offsets, g.nkeys, bp.R, ba_off);
     nl += 1;
@@ -691,7 +693,7 @@ cudaError_t msm_enqueue(cudaStream_t st, MsmWorkspace<F>& ws, const MsmGeom& g, 
       a.off_out = ba_off + (size_t)(r + 1) * (g.nkeys + 1);
       a.nkeys = g.nkeys;
       a.m = bp.m[r];
-      a.G = MSM_BA_G;
+      a.G = ba_G;
       a.inv_gcd = ba_gcd;
       a.pre = ws.ba_pre.template as<F>();
       a.key = ws.ba_key.template as<uint32_t>();

@@ -682,6 +682,7 @@ cudaError_t msm_enqueue(cudaStream_t st, MsmWorkspace<F>& ws, const MsmGeom& g, 
     uint32_t* ba_off = ws.ba_off.template as<uint32_t>();
     Affine<F>* lists[2] = {ws.ba_l0.template as<Affine<F>>(), ws.ba_l1.template as<Affine<F>>()};
     static const uint32_t ba_G = [] { const char* e = getenv("G16_BA_G"); const int v = e ? atoi(e) : (int)MSM_BA_G; return (uint32_t)((v >= 1 && v <= 4096) ? v : (int)MSM_BA_G); }();
+    static const bool ba_lean = [] { const char* e = getenv("G16_BA_LEAN"); return e && atoi(e) > 0; }();
     static const uint32_t ba_gcd = [] { const char* e = getenv("G16_BA_INV_GCD"); return (uint32_t)(e && atoi(e) > 0); }();
     ba_offsets_kernel<<<1, 1024, 0, st>>>(offsets, g.nkeys, bp.R, ba_off);
     nl += 1;
@@ -704,7 +705,8 @@ cudaError_t msm_enqueue(cudaStream_t st, MsmWorkspace<F>& ws, const MsmGeom& g, 
       const uint64_t T = ba_threads(bp.len[r + 1], a.m), lanes = (T + a.G - 1) / a.G;
       ba_forward_kernel<F><<<(unsigned)((T + 127) / 128), 128, 0, st>>>(a);
       ba_combine_kernel<F><<<(unsigned)((lanes + 31) / 32), 32, 0, st>>>(a);
-      ba_backward_kernel<F><<<(unsigned)((T + 127) / 128), 128, 0, st>>>(a);
+      if (ba_lean) ba_backward_lean_kernel<F><<<(unsigned)((T + 127) / 128), 128, 0, st>>>(a);
+      else ba_backward_kernel<F><<<(unsigned)((T + 127) / 128), 128, 0, st>>>(a);
       nl += 3;
     }
     acc_bases = lists[(bp.R - 1) & 1];

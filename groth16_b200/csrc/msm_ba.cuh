@@ -210,7 +210,68 @@ G16_HD void ba_backward(const BaRound<F>& a, uint64_t t) {
   }
 }
 
+// Same pass with the operands consumed as early as possible (x2 and y2 are folded into x1 + x2, x2 - x1 and y2 - y1
+// and dropped before the multiplications start): fewer live limbs for the Fq2 instantiation, whose straightforward
+// version above needs more than 255 registers.  Selected with G16_BA_LEAN=1 until measured on a GPU.
+template <class F>
+G16_HD void ba_backward_lean(const BaRound<F>& a, uint64_t t) {
+  const uint32_t M = a.off_out[a.nkeys];
+  const uint64_t T = ba_threads(M, a.m);
+  if (t >= T) return;
+  F run_inv = a.prod[t];
+  uint32_t kn = 0;
+  while (kn < a.m && (uint64_t)kn * T + t < M) kn++;
+  for (uint32_t k = kn; k-- > 0;) {
+    const uint32_t j = (uint32_t)((uint64_t)k * T + t);
+    const uint32_t b = a.key[j];
+    const uint32_t p = j - a.off_out[b], i0 = a.off_in[b] + 2 * p, cnt = a.off_in[b + 1] - a.off_in[b];
+    const BaSrc<F> s1 = ba_src(a, i0);
+    Affine<F> r;
+    r.x = ba_ld(&s1.p->x);
+    if (2 * p + 1 >= cnt) {          // odd one out: copy
+      r.y = ba_y(s1);
+    } else {
+      const BaSrc<F> s2 = ba_src(a, i0 + 1);
+      F sx, d;                        // x1 + x2 and the denominator
+      int kind = BA_CHORD;
+      {
+        const F x2 = ba_ld(&s2.p->x);
+        if (r.x.is_zero() || x2.is_zero() || r.x == x2) kind = ba_classify(r.x, ba_y(s1), x2, ba_y(s2), d);
+        else d = F::sub(x2, r.x);
+        sx = F::add(r.x, x2);
+      }
+      if (kind <= BA_TANGENT) {
+        F lam = F::mul(run_inv, a.pre[j]);           // 1 / d
+        run_inv = F::mul(run_inv, d);
+        r.y = ba_y(s1);
+        if (kind == BA_CHORD) {
+          lam = F::mul(F::sub(ba_y(s2), r.y), lam);
+        } else {
+          const F xx = F::sqr(r.x);
+          lam = F::mul(F::add(F::dbl(xx), xx), lam);
+        }
+        const F x3 = F::sub(F::sqr(lam), sx);        // tangent: sx = 2 x1
+        r.y = F::sub(F::mul(lam, F::sub(r.x, x3)), r.y);
+        r.x = x3;
+      } else if (kind == BA_FIRST) {
+        r.y = ba_y(s1);
+      } else if (kind == BA_SECOND) {
+        r.x = ba_ld(&s2.p->x);
+        r.y = ba_y(s2);
+      } else {
+        r = Affine<F>::inf();
+      }
+    }
+    a.out[j] = r;
+    a.ident[j] = j;
+  }
+}
+
 #ifdef __CUDACC__
+template <class F>
+__global__ void __launch_bounds__(128) ba_backward_lean_kernel(BaRound<F> a) {
+  ba_backward_lean<F>(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
 template <class F>
 __global__ void __launch_bounds__(128) ba_forward_kernel(BaRound<F> a) {
   ba_forward<F>(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);

@@ -20,7 +20,7 @@ static bool same_pt(const XYZZ<F>& a, const XYZZ<F>& b) {
 }
 
 template <class F>
-static int run_case(const Affine<F>& G, uint32_t nkeys, uint32_t nbase, uint32_t avg, int R, uint32_t m, uint32_t Gc, const char* name, uint32_t gcd = 0) {
+static int run_case(const Affine<F>& G, uint32_t nkeys, uint32_t nbase, uint32_t avg, int R, uint32_t m, uint32_t Gc, const char* name, uint32_t gcd = 0, bool lean = false) {
   int bad = 0;
   // base table: k * G, a few identities
   std::vector<Affine<F>> bases(nbase);
@@ -84,7 +84,7 @@ static int run_case(const Affine<F>& G, uint32_t nkeys, uint32_t nbase, uint32_t
     const uint64_t Tmax = ba_threads(bp.len[r + 1], m) + 3;   // over-launch like the kernels do
     for (uint64_t t = 0; t < Tmax; t++) ba_forward<F>(a, t);
     for (uint64_t l = 0; l < (Tmax + Gc - 1) / Gc + 2; l++) ba_combine<F>(a, l);
-    for (uint64_t t = 0; t < Tmax; t++) ba_backward<F>(a, t);
+    for (uint64_t t = 0; t < Tmax; t++) { if (lean) ba_backward_lean<F>(a, t); else ba_backward<F>(a, t); }
   }
   const uint32_t* offR = &off_all[(size_t)R * (nkeys + 1)];
   const std::vector<Affine<F>>& fin = lists[(R - 1) & 1];
@@ -116,6 +116,8 @@ int main() {
     }
     bad += run_case<F>(G, 1, 9, 100, 6, 32, 64, "bn254-g1-onebucket"); cases++;
     bad += run_case<F>(G, 37, 50, 12, 3, 4, 3, "bn254-g1-safegcd", 1); cases++;
+    bad += run_case<F>(G, 37, 50, 12, 3, 4, 3, "bn254-g1-lean", 0, true); cases++;
+    bad += run_case<F>(G, 5, 3, 40, 5, 8, 64, "bn254-g1-dense-lean", 1, true); cases++;
   }
   {
     using B = Fp<BLS381_FqP>;
@@ -125,6 +127,7 @@ int main() {
     bad += run_case<F>(G, 19, 20, 6, 2, 4, 5, "bls381-g2"); cases++;
     bad += run_case<F>(G, 3, 4, 20, 3, 16, 64, "bls381-g2-dense"); cases++;
     bad += run_case<F>(G, 19, 20, 6, 2, 4, 5, "bls381-g2-safegcd", 1); cases++;
+    bad += run_case<F>(G, 19, 20, 6, 3, 4, 5, "bls381-g2-lean", 1, true); cases++;
   }
   {
     using B = Fp<BLS377_FqP>;
@@ -132,6 +135,7 @@ int main() {
     auto small = [](uint32_t x) { B r = B::zero(); r.v[0] = x; return B::to_mont(r); };
     const Affine<F> G{{small(2), small(9)}, {small(4), small(1)}};
     bad += run_case<F>(G, 7, 6, 10, 2, 4, 2, "bls377-g2"); cases++;
+    bad += run_case<F>(G, 7, 6, 10, 2, 4, 2, "bls377-g2-lean", 0, true); cases++;
   }
   printf("%d cases, %d mismatches\n", cases, bad);
   return bad ? 1 : 0;

@@ -468,6 +468,13 @@ def run_cuda(a):
             "clocks": clocks,
             "setup_s": {"workload": t_work, "gpu_setup_and_key_residency": t_setup},
         }
+        knobs = {k: v for k, v in sorted(os.environ.items()) if k.startswith("G16_")}
+        if knobs:                                  # non-default tuning knobs are part of the record
+            line["config"]["env"] = knobs
+            if roof and int(knobs.get("G16_MSM_BA", "0") or 0) > 0:
+                roof["kernel"] = ("G1 bucket accumulation = batched-affine rounds (ba_forward/combine/backward) + msm_accum_l0<Fq>; "
+                                  "span of the whole stage, 4 per proof")
+                roof["traffic"] = None             # the committed ncu capture describes msm_accum_l0 without the rounds
         if sharded:
             line["sharded"] = sharded
         if roof:

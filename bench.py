@@ -42,20 +42,28 @@ def parse():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--cpu-threads", type=int, default=0, help="threads for the CPU arm / cpu_baseline (0 = all)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--inflight", type=int, default=1, choices=[1, 2],
-                    help="proofs in flight per GPU: 1 = one proof at a time (default); 2 = software pipeline over the two "
-                         "proof slots of a context (g16_prove_submit / g16_prove_wait).  Measured on B200: one proof already "
-                         "keeps the multiplier pipes busy (5 MSM streams), so pipelining gains at most ~2%% and can lose when "
-                         "two proofs' bulk kernels interleave (resident inputs) or an NCCL gather queues behind them")
+    ap.add_argument("--workload", default="synthetic", choices=["synthetic", "dummy"],
+                    help="synthetic = non-degenerate R1CS of SURVEY 8d (default, the BASELINE configs); dummy = the reference's "
+                         "own benchmark circuit, DummyCircuit with 2^log_n - 100 variables and constraints "
+                         "(benches/bench.rs:17-20,41-64): constant witness, a/b queries almost all identity")
+    ap.add_argument("--inflight", type=int, default=0, choices=[0, 1, 2],
+                    help="proofs in flight per GPU: 1 = one proof at a time; 2 = software pipeline over the two proof slots of a "
+                         "context (g16_prove_submit / g16_prove_wait); 0 (default) = 1 on one GPU (a single proof with five MSM "
+                         "streams already saturates the multiplier pipes) and 2 for the sharded multi-GPU proof (per-rank work is "
+                         "small there, the second proof fills the latency-bound tails and hides the NCCL gather)")
     ap.add_argument("--mode", default="auto", choices=["auto", "shard", "replicas"],
                     help="N > 1: 'shard' splits every MSM of ONE proof over the GPUs (strong scaling, NCCL gather of partial "
-                         "points: lowest latency); 'replicas' lets every GPU prove its own proofs (weak scaling, no "
-                         "communication: highest throughput; BASELINE config 5); 'auto' (default) measures the sharded proof "
-                         "first (reported under \"sharded\") and then reports the replica throughput as `value`")
+                         "points) and is what `value` reports; 'replicas' lets every GPU prove its own proofs (weak scaling, no "
+                         "communication: BASELINE config 5) and reports that as `value`; 'auto' (default) = 'shard' for `value` "
+                         "and additionally measures the replicas, reported under the secondary key \"replicas\"")
+    ap.add_argument("--record", default="", help="also append the JSON line to this file (profiles/r02_bench_*.json)")
     return ap.parse_args()
 
 
 def workload_name(a):
+    if a.workload == "dummy":
+        return (f"{a.curve} DummyCircuit 2^{a.log_n}-100 variables and constraints (the reference's own benchmark, "
+                "benches/bench.rs:17-20,41-64: constant witness, near-empty a/b queries), full prover path")
     return f"{a.curve} synthetic R1CS 2^{a.log_n} constraints (non-degenerate, SURVEY 8d), full A/B(G1,G2)/H/L MSM path + witness map"
 
 
@@ -148,9 +156,13 @@ def ncu_summary():
 
 # ------------------------------------------------------------------------------------------------------------------
 def build_workload(a):
-    from groth16_b200.workload import synthetic_r1cs
+    from groth16_b200.workload import dummy_r1cs, synthetic_r1cs
     t = time.time()
-    m, z, pub = synthetic_r1cs(a.curve, a.log_n, seed=a.seed)
+    if a.workload == "dummy":
+        k = (1 << a.log_n) - 100
+        m, z, pub = dummy_r1cs(a.curve, k, k, seed=a.seed)
+    else:
+        m, z, pub = synthetic_r1cs(a.curve, a.log_n, seed=a.seed)
     return m, z, pub, time.time() - t
 
 
@@ -167,97 +179,100 @@ def cpu_prove_once(a, g_codec, nq, pk, m, z, r, s, threads):
     return proof, time.time() - t, tms
 
 
-def synthetic_pk_cpu(a, m, threads):
-    """Reference arm without a GPU (this container): a key with the circuit's density pattern and pseudo-random
-    exponents, minted by the oracle's fixed-base routine.  Same prover cost as a real key; proofs are not verifiable."""
+def cpu_setup(a, m, threads):
+    """Valid CRS for the reference arm minted WITHOUT the CUDA library: the oracle's CPU trusted setup (generator.rs:47-208
+    restated in oracle/oracle.cpp) from the same toxic waste and generators as the CUDA arm, hence the very same key."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import orc
-    from groth16_b200 import CurveCodec, ProvingKey, VerifyingKey, get_curve
-    from groth16_b200.params import GENERATORS
+    from groth16_b200.api import ProvingKey, VerifyingKey     # plain dataclasses; libg16b200.so is NOT loaded by this import
+    from groth16_b200.codec import CurveCodec
+    from groth16_b200.params import GENERATORS, get_curve
     cp = get_curve(a.curve)
     cd = CurveCodec(cp)
-    nq = cd.nq
     G = GENERATORS[cp.name]
-    g1 = cd.enc_g1([G["g1"]])[0]
-    g2 = cd.enc_g2([G["g2"]])[0]
-    nv = m.num_instance_variables + m.num_witness_variables
-    n = 1 << (m.num_constraints + m.num_instance_variables - 1).bit_length()
-    rs = np.random.RandomState(7)
-
-    def rand_fr(cnt, mask=None):
-        v = rs.randint(0, 1 << 62, size=(cnt, 4), dtype=np.int64).astype(np.uint64)
-        v[:, 3] &= np.uint64((1 << 58) - 1)  # < r for all three curves; Montgomery interpretation is irrelevant here
-        if mask is not None:
-            v[~mask] = 0
-        return np.ascontiguousarray(v)
-
-    used_a = np.zeros(nv, dtype=bool); used_a[m.a[1]] = True; used_a[:m.num_instance_variables] = True
-    used_b = np.zeros(nv, dtype=bool); used_b[m.b[1]] = True
-    aq = orc.batch_mul_g1(cp.cid, nq, g1, rand_fr(nv, used_a), threads)
-    b1 = orc.batch_mul_g1(cp.cid, nq, g1, rand_fr(nv, used_b), threads)
-    b2 = orc.batch_mul_g2(cp.cid, nq, g2, rand_fr(nv, used_b), threads)
-    hq = orc.batch_mul_g1(cp.cid, nq, g1, rand_fr(n - 1), threads)
-    lq = orc.batch_mul_g1(cp.cid, nq, g1, rand_fr(m.num_witness_variables), threads)
-    single = orc.batch_mul_g1(cp.cid, nq, g1, rand_fr(3), threads)
-    single2 = orc.batch_mul_g2(cp.cid, nq, g2, rand_fr(3), threads)
-    vk = VerifyingKey(single[0], single2[0], single2[1], single2[2], None)
-    return ProvingKey(vk, single[1], single[2], aq, b1, b2, hq, lq)
+    k = orc.generate_parameters(cp.cid, cd.nq, m, cd.fr.enc(list(TOXIC)), cd.enc_g1([G["g1"]])[0], cd.enc_g2([G["g2"]])[0], threads)
+    vk = VerifyingKey(k["alpha_g1"], k["beta_g2"], k["gamma_g2"], k["delta_g2"], k["gamma_abc_g1"])
+    return ProvingKey(vk, k["beta_g1"], k["delta_g1"], k["a_query"], k["b_g1_query"], k["b_g2_query"], k["h_query"], k["l_query"])
 
 
 # ------------------------------------------------------------------------------------------------------------------
 def run_reference(a):
     """`--impl reference`: the reference's CPU implementation of the path.  ark-groth16 itself cannot be built in this
     image (no Rust toolchain, dependencies un-vendored), so the arm times oracle/oracle.cpp, the multi-threaded
-    restatement of the ark CPU prover, on all host cores; one step = one full proof of the same workload."""
+    restatement of the ark CPU prover, on all host cores; one step = one full proof of the same workload.  Nothing of the
+    CUDA library is loaded in this process: the key comes from the oracle's own CPU setup."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import orc
-    from groth16_b200 import CurveCodec, get_curve
+    from groth16_b200.codec import CurveCodec
+    from groth16_b200.params import get_curve
     threads = host_threads(a.cpu_threads)
     cp = get_curve(a.curve)
     cd = CurveCodec(cp)
     m, z, pub, _ = build_workload(a)
-    pk = None
-    kind_pk = "valid CRS minted by the GPU setup"
-    try:
-        import torch
-        if torch.cuda.is_available():
-            from groth16_b200 import Groth16
-            from groth16_b200.params import GENERATORS
-            g = Groth16(a.curve, 0)
-            G = GENERATORS[cp.name]
-            pk = g.generate_parameters_with_qap(m, *TOXIC, G["g1"], G["g2"], export=True)
-            g.close()
-    except Exception:
-        pk = None
-    if pk is None:
-        pk = synthetic_pk_cpu(a, m, threads)
-        kind_pk = "synthetic key (circuit density pattern, pseudo-random exponents) minted on the CPU"
+    t = time.time()
+    pk = cpu_setup(a, m, threads)
+    t_setup = time.time() - t
     r = cd.fr.enc1(123456789)
     s = cd.fr.enc1(987654321)
     for _ in range(a.warmup):
         cpu_prove_once(a, cd, cd.nq, pk, m, z, r, s, threads)
     t0 = time.time()
     for _ in range(a.steps):
-        cpu_prove_once(a, cd, cd.nq, pk, m, z, r, s, threads)
+        proof, _, _ = cpu_prove_once(a, cd, cd.nq, pk, m, z, r, s, threads)
     dt = time.time() - t0
     val = a.steps / dt
+    # the other CPU schedule, once, outside the timed region: ark-ec parallelises msm_bigint across windows
+    old = orc.set_msm_mode(1)
+    try:
+        proof_w, sec_w, _ = cpu_prove_once(a, cd, cd.nq, pk, m, z, r, s, threads)
+    finally:
+        orc.set_msm_mode(old)
+    assert np.array_equal(proof, proof_w), "window-parallel and chunk-parallel CPU proofs differ"
     line = {
         "impl": "reference", "metric": metric_name(a), "value": val, "unit": "proofs/s", "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u64 limbs (255-bit Fr / 381-bit Fq Montgomery integers)", "data": "synthetic",
-        "config": {"workload": workload_name(a), "curve": a.curve, "log_n": a.log_n, "pk": kind_pk},
+        "config": {"workload": workload_name(a), "curve": a.curve, "log_n": a.log_n,
+                   "pk": "valid CRS minted by the oracle's CPU setup (same toxic waste and generators as the CUDA arm: same key)",
+                   "threads": threads, "cpu_setup_s": t_setup},
         "cpu_baseline": {"value": val, "unit": "proofs/s", "cores": threads, "kind": "port",
-                         "sample": f"{a.steps} full proofs (restated ark CPU path: chunk-parallel Pippenger, radix-2 FFT)"},
+                         "sample": f"{a.steps} full proofs (restated ark CPU path: chunk-parallel Pippenger, radix-2 FFT)",
+                         "threads": threads, "chunk_parallel_s_per_proof": dt / a.steps,
+                         "ark_window_parallel_s_per_proof": sec_w,
+                         "note": "ark-ec 0.5 parallelises msm_bigint across windows (<= 256/c-way); the timed default is the "
+                                 "chunk-parallel schedule, the stronger baseline on many-core hosts; both give the same proof"},
         "e2e": {"value": val, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(a, line)
+
+
+def emit(a, line):
+    out = json.dumps(line)
+    print(out, flush=True)
+    if a.record:
+        os.makedirs(os.path.dirname(os.path.abspath(a.record)) or ".", exist_ok=True)
+        with open(a.record, "a") as f:
+            f.write(out + "\n")
 
 
 # ------------------------------------------------------------------------------------------------------------------
+def kernel_rev():
+    """hash of the kernel sources a committed ncu capture must have been taken with to describe the running code"""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("fp.cuh", "ec.cuh", "msm.cuh", "msm_ba.cuh", "fp_inv.cuh"):
+        with open(os.path.join(ROOT, "groth16_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+INT_PIPE_LANES_PER_CLK_SM = 32      # IMAD.WIDE.U32: one warp instruction per 4 cycles per SM sub-partition (4 per SM)
+
+
 def run_cuda(a):
     import torch
     import torch.distributed as dist
@@ -278,211 +293,224 @@ def run_cuda(a):
     cd = g.codec
     nq = g.nq
     G = GENERATORS[g.curve.name]
+    want_shard = world > 1 and a.mode != "replicas"
     t = time.time()
-    pk = g.generate_parameters_with_qap(m, *TOXIC, G["g1"], G["g2"],
-                                        export=((world > 1 and a.mode != "replicas") or not a.no_cpu_baseline))
-    st = {"replicas": world > 1 and a.mode == "replicas"}
-    sp = None
-    if world > 1 and not st["replicas"]:
-        from groth16_b200.dist import ShardedProver
-        sp = ShardedProver(g, pk, None, rank, world, dev)   # keep this rank's round-robin share of every query
+    pk = g.generate_parameters_with_qap(m, *TOXIC, G["g1"], G["g2"], export=(want_shard or not a.no_cpu_baseline))
     t_setup = time.time() - t
     r = np.ascontiguousarray(cd.fr.enc1(123456789))
     s = np.ascontiguousarray(cd.fr.enc1(987654321))
-    nv = m.num_instance_variables + m.num_witness_variables
     z_pinned = torch.from_numpy(z_np.view(np.int64)).pin_memory()
     z_dev = z_pinned.to(dev)
     proof = np.zeros(8 * nq, dtype=np.uint64)
-    def step(zptr, flags):
-        """one proof; returns the proof limbs (every rank computes the same proof)"""
-        if world == 1 or st["replicas"]:
-            g.prove_raw(r, s, zptr, flags, proof)
-            return proof
-        pf = sp.prove(r, s, zptr, flags)   # partial MSMs -> NCCL all_gather of 5 points per rank -> assemble
-        proof[:2 * nq] = pf.a; proof[2 * nq:6 * nq] = pf.b; proof[6 * nq:] = pf.c
-        return proof
+    ON_DEV = _lib.ASSIGNMENT_ON_DEVICE
 
-    def run_steps(zptr, flags, steps):
-        """`steps` complete proofs; with --inflight 2 proof i+1 is submitted before proof i is waited for"""
-        dev_ms, launches = [], 0
-        if a.inflight == 1:
-            for _ in range(steps):
-                step(zptr, flags)
+    class Arm:
+        """one way of running a step: 'single' (this GPU proves alone) or 'shard' (one proof split over all ranks)"""
+
+        def __init__(self, kind, inflight):
+            self.kind, self.inflight = kind, inflight
+            self.sp = None
+            if kind == "shard":
+                from groth16_b200.dist import ShardedProver
+                self.sp = ShardedProver(g, pk, None, rank, world, dev)   # keeps this rank's round-robin share of every query
+
+        def step(self, zptr, flags):
+            if self.kind == "single":
+                g.prove_raw(r, s, zptr, flags, proof)
+            else:
+                pf = self.sp.prove(r, s, zptr, flags)   # partial MSMs -> NCCL all-gather of 5 points per rank -> assemble
+                proof[:2 * nq] = pf.a; proof[2 * nq:6 * nq] = pf.b; proof[6 * nq:] = pf.c
+            return proof
+
+        def _submit(self, slot, zptr, flags):
+            if self.kind == "single":
+                g.prove_submit_raw(slot, r, s, zptr, flags)
+            else:
+                self.sp.submit(slot, r, zptr, flags)
+
+        def _finish(self, slot):
+            if self.kind == "single":
+                g.prove_wait_raw(slot, proof)
+            else:
+                pf = self.sp.finish(slot, r, s)
+                proof[:2 * nq] = pf.a; proof[2 * nq:6 * nq] = pf.b; proof[6 * nq:] = pf.c
+
+        def run_steps(self, zptr, flags, steps):
+            """`steps` complete proofs; with inflight 2 proof i+1 is submitted before proof i is waited for"""
+            dev_ms, launches = [], 0
+            if self.inflight == 1:
+                for _ in range(steps):
+                    self.step(zptr, flags)
+                    tm = g.timings()
+                    dev_ms.append(tm["total_ms"]); launches += tm["launches"]
+                return dev_ms, launches
+            self._submit(0, zptr, flags)
+            for i in range(1, steps + 1):
+                if i < steps:
+                    self._submit(i & 1, zptr, flags)
+                self._finish((i - 1) & 1)
                 tm = g.timings()
                 dev_ms.append(tm["total_ms"]); launches += tm["launches"]
             return dev_ms, launches
 
-        def submit(slot):
-            if world == 1 or st["replicas"]:
-                g.prove_submit_raw(slot, r, s, zptr, flags)
-            else:
-                sp.submit(slot, r, zptr, flags)
+        def timed(self, zptr, flags, steps, sampler=None):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            if sampler:
+                sampler.start()
+            t0 = time.perf_counter()
+            dev_ms, launches = self.run_steps(zptr, flags, steps)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            dt = time.perf_counter() - t0
+            clocks = sampler.stop() if sampler else None
+            if world > 1:
+                tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                dt = float(tt.item())
+            return dt, dev_ms, launches, clocks
 
-        def finish(slot):
-            if world == 1 or st["replicas"]:
-                g.prove_wait_raw(slot, proof)
-            else:
-                pf = sp.finish(slot, r, s)
-                proof[:2 * nq] = pf.a; proof[2 * nq:6 * nq] = pf.b; proof[6 * nq:] = pf.c
-            tm = g.timings()
-            dev_ms.append(tm["total_ms"])
-            return tm["launches"]
+        def latency(self, zptr, flags, reps=5):
+            """one proof at a time (no pipelining): wall-clock latency per proof"""
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                self.step(zptr, flags)
+            torch.cuda.synchronize()
+            return 1e3 * (time.perf_counter() - t0) / reps
 
-        submit(0)
-        for i in range(1, steps):
-            submit(i & 1)
-            launches += finish((i - 1) & 1)
-        launches += finish((steps - 1) & 1)
-        return dev_ms, launches
+        def measure(self, units, sampler=None):
+            """warm-up, resident-input run, single-proof latency, host-input (e2e) run"""
+            for _ in range(max(a.warmup, 3)):
+                self.step(z_dev.data_ptr(), ON_DEV)
+            first = self.step(z_dev.data_ptr(), ON_DEV).copy()
+            dt, dev_ms, launches, clocks = self.timed(z_dev.data_ptr(), ON_DEV, a.steps, sampler)
+            lat = self.latency(z_dev.data_ptr(), ON_DEV)
+            for _ in range(2):
+                self.step(z_pinned.data_ptr(), 0)
+            assert np.array_equal(first, proof), "resident-input and host-input proofs differ"
+            dt_e, _, _, _ = self.timed(z_pinned.data_ptr(), 0, a.steps)
+            tm_e = g.timings()
+            return {"proof": first, "value": units * a.steps / dt, "ms_per_step": 1e3 * dt / a.steps,
+                    "device_ms_per_step": statistics.mean(dev_ms), "latency_ms_single_proof": lat, "launches": int(launches),
+                    "clocks": clocks, "inflight": self.inflight,
+                    "e2e": {"value": units * a.steps / dt_e, "unit": "proofs/s", "h2d_bytes_per_step": int(tm_e["h2d_bytes"]),
+                            "d2h_bytes_per_step": int(tm_e["d2h_bytes"]), "ms_per_step": 1e3 * dt_e / a.steps}}
 
-    def timed(zptr, flags, steps, sampler=None):
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        if sampler:
-            sampler.start()
-        t0 = time.perf_counter()
-        dev_ms, launches = run_steps(zptr, flags, steps)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        dt = time.perf_counter() - t0
-        clocks = sampler.stop() if sampler else None
-        if world > 1:
-            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dt = float(tt.item())
-        return dt, dev_ms, launches, clocks
-
-    def single_latency(zptr, flags, reps=5):
-        """one proof at a time (no pipelining): wall-clock latency per proof"""
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            step(zptr, flags)
-        torch.cuda.synchronize()
-        return 1e3 * (time.perf_counter() - t0) / reps
-
-    # ---- N > 1, auto: the sharded single proof first (NCCL path), then every GPU becomes a replica ----
-    sharded = None
-    if world > 1 and a.mode == "auto":
-        for _ in range(max(a.warmup, 3)):
-            step(z_dev.data_ptr(), _lib.ASSIGNMENT_ON_DEVICE)
-        shard_proof = step(z_dev.data_ptr(), _lib.ASSIGNMENT_ON_DEVICE).copy()
-        dt_s, dev_s, _, _ = timed(z_dev.data_ptr(), _lib.ASSIGNMENT_ON_DEVICE, a.steps)
-        step(z_pinned.data_ptr(), 0)
-        dt_s2, _, _, _ = timed(z_pinned.data_ptr(), 0, a.steps)
-        sharded = {"mode": f"msm-shard{world}: one proof per step, pair i of every MSM on rank i mod {world}, NCCL all_gather of 5 "
-                           "partial points per rank", "scaling": "strong", "value": a.steps / dt_s, "unit": "proofs/s",
-                   "latency_ms": 1e3 * dt_s / a.steps, "device_ms_per_step": statistics.mean(dev_s),
-                   "e2e_value": a.steps / dt_s2}
-        g.load_proving_key(pk, 0, 1)          # full key resident again: every rank proves on its own from here on
-        st["replicas"] = True
-    replicas = st["replicas"]
-    # ---- warm-up, then the resident-input measurement (`value`) ----
-    for _ in range(max(a.warmup, 3)):
-        step(z_dev.data_ptr(), _lib.ASSIGNMENT_ON_DEVICE)
-    first = step(z_dev.data_ptr(), _lib.ASSIGNMENT_ON_DEVICE).copy()
-    if sharded is not None:
-        assert np.array_equal(first, shard_proof), "sharded and single-GPU proofs differ"
     sampler = ClockSampler(local) if rank == 0 else None
-    dt, dev_ms, launches, clocks = timed(z_dev.data_ptr(), _lib.ASSIGNMENT_ON_DEVICE, a.steps, sampler)
-    units = world if replicas else 1          # proofs completed per step across the job
-    value = units * a.steps / dt
-    lat_ms = single_latency(z_dev.data_ptr(), _lib.ASSIGNMENT_ON_DEVICE)
-    # ---- end to end through the public call with HOST buffers: pinned assignment in, proof out ----
-    for _ in range(2):
-        step(z_pinned.data_ptr(), 0)
-    dt_e2e, _, _, _ = timed(z_pinned.data_ptr(), 0, a.steps)
-    e2e_proof = proof.copy()
-    tm_e2e = g.timings()
-    assert np.array_equal(first, e2e_proof), "resident-input and host-input proofs differ"
+    secondary = None
+    if want_shard:
+        arm = Arm("shard", a.inflight or 2)
+        main = arm.measure(1, sampler)
+        par = (f"msm-shard{world}: one proof per step, pair i of every MSM on rank i mod {world}, witness map replicated, "
+               "5 partial points per rank all-gathered over NCCL, every rank assembles the same proof")
+        scaling = "strong"
+        if a.mode == "auto":
+            g.load_proving_key(pk, 0, 1)          # full key resident again: every rank proves on its own
+            rep = Arm("single", a.inflight or 1).measure(world)
+            assert np.array_equal(rep["proof"], main["proof"]), "sharded and single-GPU proofs differ"
+            secondary = {"mode": f"replicas{world}: one independent proof per GPU per step, no communication", "scaling": "weak",
+                         "value": rep["value"], "unit": "proofs/s", "ms_per_step": rep["ms_per_step"], "e2e_value": rep["e2e"]["value"],
+                         "proof_equals_sharded_proof": True}
+    else:
+        arm = Arm("single", a.inflight or 1)
+        main = arm.measure(world, sampler)
+        par = f"replicas{world} (one independent proof per GPU per step, no communication)" if world > 1 else "single-gpu"
+        scaling = "weak" if world > 1 else "strong"
+    first = main["proof"]
 
-    line = None
     if rank == 0:
-        # ---- kernel-level numbers: serialised MSMs so that CUDA events bracket one kernel at a time ----
-        roof = None
-        kern = {}
+        # ---- kernel-level numbers: serialised MSMs so that CUDA events bracket one bucket-accumulation stage at a time ----
+        roof, kern, cpu = None, {}, None
         if world == 1:
             acc = {k: [] for k in ("h", "l", "a", "b_g1", "b_g2")}
-            pairs = None
             for _ in range(3):
-                g.prove_raw(r, s, z_dev.data_ptr(), _lib.ASSIGNMENT_ON_DEVICE | _lib.SERIAL_MSMS, proof)
+                g.prove_raw(r, s, z_dev.data_ptr(), ON_DEV | _lib.SERIAL_MSMS, proof)
                 tm = g.timings()
-                pairs = tm["msm_pairs"]
                 for k in acc:
                     acc[k].append(tm["msm_accum_ms"][k])
-                wm_ms = tm["witness_map_ms"]
+            assert np.array_equal(first, proof), "serialised-stream proof differs"
+            pairs, entries, wm_ms = tm["msm_pairs"], tm["msm_entries"], tm["witness_map_ms"]
             g1_bytes = 32 + 2 * 8 * nq          # scalar + packed affine G1 base  (SURVEY 8d: 128 B on BLS12-381)
             g2_bytes = 32 + 4 * 8 * nq          # 224 B
-            t_g1 = sum(statistics.median(acc[k]) for k in ("h", "l", "a", "b_g1"))
-            b_g1 = sum(pairs[k] for k in ("h", "l", "a", "b_g1")) * g1_bytes
+            g1k = [k for k in ("h", "l", "a", "b_g1") if pairs[k]]
+            t_g1 = sum(statistics.median(acc[k]) for k in g1k)
+            b_g1 = sum(pairs[k] for k in g1k) * g1_bytes
             t_g2 = statistics.median(acc["b_g2"])
             b_g2 = pairs["b_g2"] * g2_bytes
             peak, peak_src = measured_peak_hbm()
             summ = ncu_summary() or {}
-            ach = b_g1 / (t_g1 * 1e-3) / 1e9
-            roof = {"kernel": "msm_accum_l0<Fq> (G1 bucket accumulation; 4 launches per proof, largest share of the step)",
-                    "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": summ.get("g1_dram_bytes_per_launch"),
-                    "algorithmic_bytes_per_launch": b_g1 / 4, "avg_launch_ms": t_g1 / 4, "peak_source": peak_src,
-                    "note": "integer-multiply bound, not HBM bound: ncu reports the FMA-heavy (IMAD.WIDE) pipe at "
-                            f"{summ.get('g1_fmaheavy_pct', 'n/a')}% of peak for this kernel (profiles/)"}
+            cfg = g.config()
+            same_code = summ.get("kernel_rev") == kernel_rev() and summ.get("config") == cfg
+            ach = b_g1 / (t_g1 * 1e-3) / 1e9 if t_g1 > 0 else 0.0
+            # honest bound: the integer-multiply pipe.  IMAD.WIDE per bucket entry from the SASS (cuobjdump, DESIGN.md section 3)
+            nl = 2 * nq                          # 32-bit limbs of Fq
+            mul = 2 * nl * nl                    # IMAD.WIDE per Montgomery product (288 for 12 limbs, 128 for 8)
+            per_entry = cfg["imad_per_g1_entry_mul"] * mul
+            e_g1 = sum(entries[k] for k in g1k)
+            sm_clk = (main["clocks"] or {}).get("sm_mhz") or 1965.0
+            pipe_peak = torch.cuda.get_device_properties(dev).multi_processor_count * INT_PIPE_LANES_PER_CLK_SM * sm_clk * 1e6
+            imad_rate = e_g1 * per_entry / (t_g1 * 1e-3) if t_g1 > 0 else 0.0
+            roof = {"kernel": cfg["g1_accum_stage"], "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": ach / peak, "traffic": summ.get("g1_dram_bytes_per_launch") if same_code else None,
+                    "algorithmic_bytes_per_launch": b_g1 / max(1, len(g1k)), "avg_launch_ms": t_g1 / max(1, len(g1k)),
+                    "launches_averaged": len(g1k), "peak_source": peak_src,
+                    "int_pipe_frac": imad_rate / pipe_peak, "int_pipe_imad_wide_per_s": imad_rate, "int_pipe_peak_per_s": pipe_peak,
+                    "int_pipe_model": f"{e_g1} bucket entries x {cfg['imad_per_g1_entry_mul']:.2f} field products x {mul} IMAD.WIDE "
+                                      f"per product; peak = SMs x 32 lanes/clk x {sm_clk:.0f} MHz",
+                    "note": "integer-multiply bound, not HBM bound: algorithmic bytes are 128 B per pair against ~2-3 thousand "
+                            "IMAD.WIDE; `traffic` is the ncu dram__bytes of the committed capture when it was taken with this "
+                            "code and configuration, else null"}
             n_dom = 1 << a.log_n
-            kern = {"msm_accum_l0_g2": {"achieved_gbs": b_g2 / (t_g2 * 1e-3) / 1e9, "launch_ms": t_g2,
-                                        "frac": b_g2 / (t_g2 * 1e-3) / 1e9 / peak},
+            kern = {"g2_accum_stage": {"achieved_gbs": b_g2 / (t_g2 * 1e-3) / 1e9 if t_g2 > 0 else None, "launch_ms": t_g2,
+                                       "frac": (b_g2 / (t_g2 * 1e-3) / 1e9 / peak) if t_g2 > 0 else None},
                     "witness_map": {"ms": wm_ms, "achieved_gbs": 576 * n_dom / (wm_ms * 1e-3) / 1e9,
-                                    "frac": 576 * n_dom / (wm_ms * 1e-3) / 1e9 / peak}}
-        # ---- CPU baseline beside it (rank 0, N = 1): one full proof by the restated ark CPU path, also a parity check ----
-        cpu = None
-        if world == 1 and not a.no_cpu_baseline:
-            sys.path.insert(0, os.path.join(ROOT, "oracle"))
-            import orc
-            threads = host_threads(a.cpu_threads)
-            cproof, csec, tms = cpu_prove_once(a, cd, nq, pk, m, z_np, r, s, threads)
-            if not np.array_equal(cproof, first):
-                raise SystemExit("PARITY FAILURE: CUDA proof != CPU oracle proof at full size")
-            cpu = {"value": 1.0 / csec, "unit": "proofs/s", "cores": threads, "kind": "port",
-                   "sample": f"1 full proof of the same workload ({csec:.2f} s wall: witness map {tms[0]:.0f} ms, MSMs+assembly "
-                             f"{tms[1]:.0f} ms), restated ark CPU path; proof bit-identical to the CUDA proof"}
+                                    "frac": 576 * n_dom / (wm_ms * 1e-3) / 1e9 / peak},
+                    "msm_accum_ms": {k: statistics.median(v) for k, v in acc.items()}, "msm_pairs": pairs, "msm_entries": entries}
+            # ---- CPU baseline beside it (rank 0, N = 1): one full proof by the restated ark CPU path, also a parity check ----
+            if not a.no_cpu_baseline:
+                threads = host_threads(a.cpu_threads)
+                cproof, csec, tms = cpu_prove_once(a, cd, nq, pk, m, z_np, r, s, threads)
+                if not np.array_equal(cproof, first):
+                    raise SystemExit("PARITY FAILURE: CUDA proof != CPU oracle proof at full size")
+                cpu = {"value": 1.0 / csec, "unit": "proofs/s", "cores": threads, "kind": "port",
+                       "sample": f"1 full proof of the same workload ({csec:.2f} s wall: witness map {tms[0]:.0f} ms, MSMs+assembly "
+                                 f"{tms[1]:.0f} ms), restated ark CPU path; proof bit-identical to the CUDA proof"}
         line = {
-            "metric": metric_name(a), "value": value, "unit": "proofs/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
-            "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak" if replicas else "strong",
+            "metric": metric_name(a), "value": main["value"], "unit": "proofs/s", "n_gpus": world, "steps": a.steps,
+            "warmup": max(a.warmup, 3), "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None,
             "dtype": "u32 limbs (255-bit Fr / 381-bit Fq Montgomery integers)", "data": "synthetic",
-            "config": {"workload": workload_name(a), "curve": a.curve, "log_n": a.log_n,
-                       "parallelism": (f"replicas{world} (one independent proof per GPU per step)" if replicas else
-                                       f"msm-shard{world} (one proof per step, MSM pairs split by index range)") if world > 1 else "single-gpu",
-                       "inflight": a.inflight,
+            "config": {"workload": workload_name(a), "curve": a.curve, "log_n": a.log_n, "parallelism": par,
+                       "inflight": main["inflight"], "library": g.config(),
                        "l2": "inputs exceed L2: resident proving key with precomputed multiples (GBs) + 32 MiB assignment + "
                              "sorted digit arrays (134 MB per MSM) are streamed every step",
                        "timing": "wall clock around K complete proofs bracketed by barrier+synchronize (host finish/assembly "
                                  "included), max over ranks; with inflight=2 proof i+1 is submitted before proof i is waited "
                                  "for (two proof slots per context); device_ms_per_step = CUDA-event span of one proof's GPU "
                                  "work; latency_ms_single_proof = one proof at a time"},
-            "device_ms_per_step": statistics.mean(dev_ms),
-            "latency_ms_single_proof": lat_ms,
-            "e2e": {"value": units * a.steps / dt_e2e, "unit": "proofs/s", "h2d_bytes_per_step": int(tm_e2e["h2d_bytes"]),
-                    "d2h_bytes_per_step": int(tm_e2e["d2h_bytes"]), "ms_per_step": 1e3 * dt_e2e / a.steps},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
+            "device_ms_per_step": main["device_ms_per_step"],
+            "latency_ms_single_proof": main["latency_ms_single_proof"],
+            "e2e": main["e2e"],
+            "gpu_launches": main["launches"],
+            "clocks": main["clocks"],
             "setup_s": {"workload": t_work, "gpu_setup_and_key_residency": t_setup},
         }
         knobs = {k: v for k, v in sorted(os.environ.items()) if k.startswith("G16_")}
         if knobs:                                  # non-default tuning knobs (INTEGRATION.md section 6) are part of the record
             line["config"]["env"] = knobs
-            if roof and int(knobs.get("G16_MSM_BA", "0") or 0) > 0:
-                roof["kernel"] = ("G1 bucket accumulation = batched-affine rounds (ba_forward/combine/backward) + msm_accum_l0<Fq>; "
-                                  "span of the whole stage, 4 per proof")
-                roof["traffic"] = None             # the committed ncu capture describes msm_accum_l0 without the rounds
-        if sharded:
-            line["sharded"] = sharded
+        if secondary:
+            line["replicas"] = secondary
         if roof:
             line["roofline"] = roof
             line["kernels"] = kern
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        emit(a, line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -30,8 +30,13 @@ class PkExportDesc(C.Structure):
 class Timings(C.Structure):
     _fields_ = [("total_ms", C.c_float), ("h2d_ms", C.c_float), ("witness_map_ms", C.c_float),
                 ("msm_ms", C.c_float * 5), ("msm_accum_ms", C.c_float * 5), ("host_finish_ms", C.c_float),
-                ("msm_pairs", C.c_uint64 * 5), ("launches", C.c_uint64), ("h2d_bytes", C.c_uint64),
-                ("d2h_bytes", C.c_uint64)]
+                ("msm_pairs", C.c_uint64 * 5), ("msm_entries", C.c_uint64 * 5), ("launches", C.c_uint64),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+
+
+class Config(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("c", "ne", "copies", "k0_g1", "k0_g2", "ba_rounds_g1", "ba_rounds_g2", "ba_m", "ba_g",
+                                         "ba_inv_gcd", "acc_block", "sm_count", "rank", "world")] + [("reserved", C.c_int32 * 4)]
 
 
 # every symbol include/g16b200.h declares: (name, restype, argtypes)
@@ -60,6 +65,8 @@ SIGNATURES = [
     ("g16_prove_partial_wait", C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     ("g16_witness_map", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
     ("g16_get_timings", C.c_int, [C.c_void_p, C.POINTER(Timings)]),
+    ("g16_get_config", C.c_int, [C.c_void_p, C.POINTER(Config)]),
+    ("g16_set_option", C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
 ]
 
 G16_OK = 0

@@ -142,6 +142,7 @@ class Groth16:
         self.nq = self._lib.g16_fq_limbs(self._ctx)
         self._matrices: Optional[ConstraintMatrices] = None
         self._pk_resident = False
+        self._pk_obj: Optional[ProvingKey] = None   # identity of the resident key (None: minted by g16_setup and not exported)
         self.world = 1
 
     def close(self):
@@ -167,7 +168,12 @@ class Groth16:
         return v
 
     def ntt_log(self, log_n: int, values: np.ndarray, inverse=False, coset=False) -> np.ndarray:
+        """Same transform with the domain size given explicitly (error-path tests: log_n above the two-adicity).  The C side
+        copies 32 << log_n bytes in and out of `values`, so the length is checked here."""
         v = np.ascontiguousarray(values, dtype=np.uint64).reshape(-1, 4).copy()
+        if log_n < 0 or (log_n <= self.curve.two_adicity and v.shape[0] != (1 << log_n)):
+            raise ValueError(f"values must hold exactly 2^{log_n} field elements")
+        # log_n above the two-adicity: the C side returns PolynomialDegreeTooLarge before it touches the buffer
         _check(self._lib.g16_ntt(self._ctx, log_n, int(inverse), int(coset), _ptr(v)))
         return v
 
@@ -240,6 +246,7 @@ class Groth16:
                                           C.byref(structs[2])))
         self._matrices = m
         self._pk_resident = False
+        self._pk_obj = None
 
     def load_proving_key(self, pk: ProvingKey, rank: int = 0, world: int = 1):
         d = _lib.PkDesc()
@@ -258,6 +265,7 @@ class Groth16:
             setattr(d, k, _u64p(arrs[k]))
         _check(self._lib.g16_pk_load(self._ctx, C.byref(d), rank, world))
         self._pk_resident = True
+        self._pk_obj = pk
         self.world = world
 
     # ---- generator.rs:47-208 with explicit toxic waste and generators ----
@@ -272,7 +280,8 @@ class Groth16:
         _check(self._lib.g16_setup(self._ctx, *[_ptr(x) for x in sc], _ptr(g1), _ptr(g2)))
         self._pk_resident = True
         self.world = 1
-        return self.export_proving_key() if export else None
+        self._pk_obj = self.export_proving_key() if export else None
+        return self._pk_obj
 
     def export_proving_key(self) -> ProvingKey:
         m = self._matrices
@@ -301,7 +310,8 @@ class Groth16:
         to reuse what is already resident on the GPU."""
         if matrices is not None and matrices is not self._matrices:
             self.load_matrices(matrices)
-        if pk is not None and not self._pk_resident:
+        # the reference always proves under the `pk` argument (prover.rs:26): a key other than the resident one is loaded
+        if pk is not None and (not self._pk_resident or pk is not self._pk_obj):
             self.load_proving_key(pk)
         m = self._matrices
         if m is None or not self._pk_resident:
@@ -378,8 +388,29 @@ class Groth16:
                     msm_ms={n: t.msm_ms[i] for i, n in enumerate(names)},
                     msm_accum_ms={n: t.msm_accum_ms[i] for i, n in enumerate(names)},
                     msm_pairs={n: int(t.msm_pairs[i]) for i, n in enumerate(names)},
+                    msm_entries={n: int(t.msm_entries[i]) for i, n in enumerate(names)},
                     host_finish_ms=t.host_finish_ms, launches=int(t.launches), h2d_bytes=int(t.h2d_bytes),
                     d2h_bytes=int(t.d2h_bytes))
+
+    def set_option(self, key: str, value: int):
+        """MSM launch-geometry knobs (g16_set_option; results never depend on them)."""
+        _check(self._lib.g16_set_option(self._ctx, key.encode(), int(value)))
+
+    def config(self) -> dict:
+        """Launch geometry of the resident key's MSMs plus two derived figures bench.py reports: the field products per
+        bucket entry of the G1 accumulation stage (XYZZ mixed addition = 10; batched-affine addition = 6 + the combine's
+        share) and the stage's name."""
+        c = _lib.Config()
+        _check(self._lib.g16_get_config(self._ctx, C.byref(c)))
+        d = {n: int(getattr(c, n)) for n, _ in _lib.Config._fields_ if n != "reserved"}
+        R = d["ba_rounds_g1"]
+        ba_mul = 6.0 + 3.0 / max(1, d["ba_m"])            # forward 1 + backward 5 + combine 3 per thread product
+        frac = 1.0 - 0.5 ** R
+        d["imad_per_g1_entry_mul"] = frac * ba_mul + (1.0 - frac) * 10.0 if R > 0 else 10.0
+        d["g1_accum_stage"] = (f"G1 bucket accumulation: {R} batched-affine rounds (ba_forward / ba_combine / ba_backward) + "
+                               "msm_accum_l0<Fq> on the last list; one stage per G1 MSM" if R > 0 else
+                               "msm_accum_l0<Fq> (G1 bucket accumulation, XYZZ mixed additions); one launch per G1 MSM")
+        return d
 
     def _fr_arg(self, x) -> np.ndarray:
         if isinstance(x, (int, np.integer)):

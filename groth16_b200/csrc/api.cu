@@ -131,4 +131,14 @@ int g16_get_timings(const g16_ctx* ctx, g16_timings* out) {
   return G16_OK;
 }
 
+int g16_get_config(const g16_ctx* ctx, g16_config* out) {
+  CTX_OR_FAIL(ctx);
+  return ctx->eng->get_config(out);
+}
+int g16_set_option(g16_ctx* ctx, const char* key, int64_t value) {
+  CTX_OR_FAIL(ctx);
+  if (!key) return fail(G16_ERR_BAD_ARGUMENT, "null key");
+  return ctx->eng->set_option(key, (long long)value);
+}
+
 }  // extern "C"

@@ -5,10 +5,17 @@
 // msm.cuh, the O(1) tail (six scalar multiplications, sums, into_affine) runs on the host with the same field code.
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>       // header-only NVTX v3: no-ops unless a profiler injects itself
+#include <nvtx3/nvToolsExtCudaRt.h>
 #include <algorithm>
 #include <chrono>
 #include <cstdlib>
 #include <cstdio>
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -31,6 +38,68 @@ inline int fail(int code, const std::string& msg) {
       return fail(G16_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(_e) + " @" + __FILE__ + ":" + \
                                     std::to_string(__LINE__));                                            \
   } while (0)
+
+// NVTX ranges named after the reference's own `start_timer!` spans (prover.rs:35,36,62,89,99,111,119),
+// so a Nsight timeline of this library reads like ark's `print-trace` output.  Host ranges bracket the enqueue of each
+// stage; the CUDA streams carry the same names, which is where the asynchronous GPU work of the stage shows up.
+struct NvtxSpan {
+  explicit NvtxSpan(const char* name) { nvtxRangePushA(name); }
+  ~NvtxSpan() { nvtxRangePop(); }
+};
+static constexpr const char* SPAN_PROVER = "Groth16::Prover";                 // prover.rs:35
+static constexpr const char* SPAN_WITNESS_MAP = "R1CS to QAP witness map";    // prover.rs:36
+static constexpr const char* SPAN_C = "Compute C";                            // prover.rs:62  (H and L MSMs, r*s*delta)
+static constexpr const char* SPAN_A = "Compute A";                            // prover.rs:89
+static constexpr const char* SPAN_B1 = "Compute B in G1";                     // prover.rs:99
+static constexpr const char* SPAN_B2 = "Compute B in G2";                     // prover.rs:111
+static constexpr const char* SPAN_FINISH_C = "Finish C";                      // prover.rs:119
+
+// Persistent host workers of one context (one per MSM stream + one for the (r, s)-only scalar multiplications): a proof
+// used to spawn and join six std::threads (visible as host-side contention with 8 replica processes per box).
+class HostPool {
+ public:
+  struct Ticket {   // completion handle of one task
+    std::mutex m;
+    std::condition_variable cv;
+    bool done = false;
+    void wait() { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return done; }); }
+  };
+  explicit HostPool(int n) {
+    for (int i = 0; i < n; i++) th_.emplace_back([this] { run(); });
+  }
+  ~HostPool() {
+    { std::lock_guard<std::mutex> l(m_); stop_ = true; }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  std::shared_ptr<Ticket> submit(std::function<void()> fn) {
+    auto tk = std::make_shared<Ticket>();
+    { std::lock_guard<std::mutex> l(m_); q_.emplace_back(std::move(fn), tk); }
+    cv_.notify_one();
+    return tk;
+  }
+ private:
+  void run() {
+    for (;;) {
+      std::pair<std::function<void()>, std::shared_ptr<Ticket>> job;
+      {
+        std::unique_lock<std::mutex> l(m_);
+        cv_.wait(l, [&] { return stop_ || !q_.empty(); });
+        if (q_.empty()) return;
+        job = std::move(q_.front());
+        q_.pop_front();
+      }
+      job.first();
+      { std::lock_guard<std::mutex> l(job.second->m); job.second->done = true; }
+      job.second->cv.notify_all();
+    }
+  }
+  std::vector<std::thread> th_;
+  std::mutex m_;
+  std::condition_variable cv_;
+  std::deque<std::pair<std::function<void()>, std::shared_ptr<Ticket>>> q_;
+  bool stop_ = false;
+};
 
 struct IEngine {
   virtual ~IEngine() {}
@@ -55,6 +124,8 @@ struct IEngine {
   virtual int partial_wait(int slot, uint64_t* partial) = 0;
   virtual int witness_map(const uint64_t* z, uint32_t flags, uint64_t* h) = 0;
   virtual uint32_t domain_log() const = 0;
+  virtual int set_option(const char* key, long long value) = 0;
+  virtual int get_config(g16_config* out) const = 0;
   g16_timings tm{};
 };
 
@@ -71,6 +142,15 @@ struct Engine : IEngine {
   static constexpr int NQ64 = Fq::N / 2;
   static constexpr int FR_BITS = CP::FrP::BITS;
   enum { M_H = 0, M_L = 1, M_A = 2, M_B1 = 3, M_B2 = 4 };
+  static const char* span_of(int m) {
+    switch (m) {
+      case M_H: return "Compute C: h_query MSM";
+      case M_L: return "Compute C: l_query MSM";
+      case M_A: return SPAN_A;
+      case M_B1: return SPAN_B1;
+      default: return SPAN_B2;
+    }
+  }
 
   int device = 0;
   // Everything one in-flight proof owns: streams, events, work vectors, MSM workspaces, timings.  Two slots allow a
@@ -90,13 +170,17 @@ struct Engine : IEngine {
     MsmGeom geom[5] = {};
     Fr r, s;
     FixedMuls fx;
-    std::thread helper;
+    std::shared_ptr<HostPool::Ticket> helper;   // (r, s)-only scalar multiplications in flight on the pool
     unsigned long long launches0 = 0;
   };
   static constexpr int NSLOTS = 2;
   Slot slots[NSLOTS];
   Slot& S0 = slots[0];   // slot used by the synchronous entry points
-  NttDomain<Fr> dom;
+  std::unique_ptr<HostPool> pool;   // 5 MSM finishers + 2 helpers, alive for the context's lifetime
+  NttDomain<Fr> dom;       // domain of the RESIDENT circuit (size 2^L); only circuit_load / the prover touch it
+  NttDomain<Fr> dom_api;   // domain of the stand-alone g16_ntt / g16_witness_map_evals calls (any size): kept apart so that
+                           // an NTT of another size between circuit_load and prove cannot leave the prover with the wrong
+                           // twiddles (the two used to share `dom`)
   MsmCounters ctr;
   unsigned long long ntt_launches = 0;
 
@@ -117,10 +201,22 @@ struct Engine : IEngine {
     uint64_t lo = 0, hi = 0;   // this rank owns pairs lo, lo + world, lo + 2 world, ... : hi - lo of them (lo = rank)
     MsmGeom geom{};
   } q[5];
-  // MSM tuning knobs (environment: G16_MSM_C, G16_MSM_NE, G16_MSM_MAXCOPIES)
+  // MSM tuning knobs: defaults below, overridden at context creation by the environment (G16_MSM_C, G16_MSM_NE,
+  // G16_MSM_MAXCOPIES, G16_MSM_BA, G16_MSM_BA_G2, G16_BA_M, G16_BA_G, G16_BA_INV_GCD, G16_ACC_K0_G1, G16_ACC_K0_G2,
+  // G16_ACC_BLOCK) and at run time by g16_set_option (same names, lower case, without the G16_ prefix).
   int cfg_c = 0;          // 0 = pick from n
   int cfg_ne = 1;         // effective windows with precomputed bases; 0 = no precomputation
   int cfg_maxcopies = MSM_MAX_COPIES;
+  struct Tune {
+    int ba_g1 = 4;        // batched-affine rounds before the XYZZ accumulation, G1 MSMs with >= 2^18 entries
+    int ba_g2 = 0;        // same for the G2 MSM
+    int ba_m = 16;        // additions per thread and round
+    int ba_G = 64;        // thread products per inversion
+    int ba_gcd = 1;       // safegcd inversion
+    int k0_g1 = 0;        // sorted entries per accumulation thread (0 = automatic)
+    int k0_g2 = 0;
+    int acc_block = 128;
+  } tune;
   MsmGeom pick_geom(uint64_t cnt) const {
     if (cfg_ne <= 0) return msm_geom(cnt, FR_BITS, cfg_c, 0);
     // with all windows sharing one bucket set the bucket count is 2^(c-1) whatever the size: c = 16 from 2^16 pairs up
@@ -133,17 +229,73 @@ struct Engine : IEngine {
   }
   // entries per level-0 thread, from the number of resident accumulation threads of this device
   int sm_count = 148;
+  bool ba_allowed = true;   // cleared by pk_load / setup when the rounds' work lists would not fit in device memory
   MsmGeom with_k0(MsmGeom g, bool g2) const {
     g.k0 = msm_pick_k0(g.max_entries, (uint64_t)sm_count * 128 * (g2 ? 2 : 3), g2 ? 16 : 8);
     // G2 additions are ~3x longer: 32 entries per thread (twice the thread count) shortens the last partial wave (-13 %)
     if (g2 && g.k0 > 32) g.k0 = 32;
-    if (const char* v = getenv(g2 ? "G16_ACC_K0_G2" : "G16_ACC_K0_G1")) { const int k = atoi(v); if (k >= 4 && k <= 1024) g.k0 = k; }
-    // experimental batched-affine pre-reduction (msm_ba.cuh): rounds for G1 / G2 MSMs with at least 2^18 entries
-    if (const char* v = getenv(g2 ? "G16_MSM_BA_G2" : "G16_MSM_BA")) {
-      const int r = atoi(v);
-      if (r > 0 && r <= MSM_BA_MAX_ROUNDS && g.max_entries >= (1u << 18)) g.ba = r;
-    }
+    const int k = g2 ? tune.k0_g2 : tune.k0_g1;
+    if (k >= 4 && k <= 1024) g.k0 = k;
+    // batched-affine pre-reduction (msm_ba.cuh) for MSMs with at least 2^18 entries
+    const int r = g2 ? tune.ba_g2 : tune.ba_g1;
+    g.ba = (ba_allowed && r > 0 && g.max_entries >= (1u << 18)) ? std::min(r, (int)MSM_BA_MAX_ROUNDS) : 0;
+    g.ba_m = tune.ba_m;
+    g.ba_G = tune.ba_G;
+    g.ba_gcd = tune.ba_gcd;
+    g.acc_block = tune.acc_block;
     return g;
+  }
+  void refresh_geoms() {   // after a knob changed: same shards, new launch geometry
+    for (int m = 0; m < 5; m++)
+      if (q[m].hi > q[m].lo) q[m].geom = with_k0(q[m].geom, m == M_B2);
+  }
+  // Work lists of the batched-affine rounds for all five MSMs of one proof slot; the rounds are switched off for this
+  // key when two slots' worth would not fit next to the resident key (e.g. 2^24 constraints on one GPU).
+  void decide_ba_memory() {
+    ba_allowed = true;
+    refresh_geoms();
+    uint64_t need = 0;
+    for (int m = 0; m < 5; m++) {
+      if (q[m].hi <= q[m].lo) continue;
+      MsmBaPlan bp;
+      bp.make(q[m].geom);
+      need += (m == M_B2) ? bp.template extra_bytes<Fq2>() : bp.template extra_bytes<Fq>();
+      need += bp.len[0] * 8;
+    }
+    size_t fr = 0, tot = 0;
+    if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) return;
+    if (2 * need + (4ull << 30) > fr) {
+      ba_allowed = false;
+      refresh_geoms();
+    }
+  }
+  int set_option(const char* key, long long v) override {
+    if (any_busy()) return fail(G16_ERR_BAD_ARGUMENT, "a proof is in flight");
+    const std::string k(key ? key : "");
+    if (k == "msm_ba") tune.ba_g1 = (int)v;
+    else if (k == "msm_ba_g2") tune.ba_g2 = (int)v;
+    else if (k == "ba_m") tune.ba_m = (int)std::max(1ll, std::min(v, 256ll));
+    else if (k == "ba_g") tune.ba_G = (int)std::max(1ll, std::min(v, 4096ll));
+    else if (k == "ba_inv_gcd") tune.ba_gcd = v ? 1 : 0;
+    else if (k == "acc_k0_g1") tune.k0_g1 = (int)v;
+    else if (k == "acc_k0_g2") tune.k0_g2 = (int)v;
+    else if (k == "acc_block") tune.acc_block = (int)v;
+    else return fail(G16_ERR_BAD_ARGUMENT, "unknown option: " + k);
+    refresh_geoms();
+    return G16_OK;
+  }
+  int get_config(g16_config* o) const override {
+    if (!o) return fail(G16_ERR_BAD_ARGUMENT, "null");
+    memset(o, 0, sizeof(*o));
+    const MsmGeom& g1 = q[M_H].geom;
+    const MsmGeom& g2 = q[M_B2].geom;
+    o->c = g1.c; o->ne = g1.ne; o->copies = g1.copies;
+    o->k0_g1 = g1.k0; o->k0_g2 = g2.k0;
+    o->ba_rounds_g1 = g1.ba; o->ba_rounds_g2 = g2.ba;
+    o->ba_m = tune.ba_m; o->ba_g = tune.ba_G; o->ba_inv_gcd = tune.ba_gcd; o->acc_block = tune.acc_block;
+    o->sm_count = sm_count;
+    o->world = (int32_t)world; o->rank = (int32_t)rank;
+    return G16_OK;
   }
   template <class F>
   int finish_query(Query& x) {   // x.bases holds copy 0; build the other copies and the infinity mask
@@ -169,9 +321,21 @@ struct Engine : IEngine {
     G16_CUDA(cudaGetDeviceProperties(&prop, dev));
     if (prop.major < 10) return fail(G16_ERR_CUDA, "device is not sm_100-class (this library ships sm_100a code only)");
     sm_count = prop.multiProcessorCount;
+    pool.reset(new HostPool(7));
     if (const char* v = getenv("G16_MSM_C")) cfg_c = atoi(v);
     if (const char* v = getenv("G16_MSM_NE")) cfg_ne = atoi(v);
     if (const char* v = getenv("G16_MSM_MAXCOPIES")) cfg_maxcopies = std::max(1, std::min(atoi(v), (int)MSM_MAX_COPIES));
+    auto env_int = [](const char* name, int& dst, int lo, int hi) {
+      if (const char* v = getenv(name)) { const int x = atoi(v); if (x >= lo && x <= hi) dst = x; }
+    };
+    env_int("G16_MSM_BA", tune.ba_g1, 0, MSM_BA_MAX_ROUNDS);
+    env_int("G16_MSM_BA_G2", tune.ba_g2, 0, MSM_BA_MAX_ROUNDS);
+    env_int("G16_BA_M", tune.ba_m, 1, 256);
+    env_int("G16_BA_G", tune.ba_G, 1, 4096);
+    env_int("G16_BA_INV_GCD", tune.ba_gcd, 0, 1);
+    env_int("G16_ACC_K0_G1", tune.k0_g1, 4, 1024);
+    env_int("G16_ACC_K0_G2", tune.k0_g2, 4, 1024);
+    env_int("G16_ACC_BLOCK", tune.acc_block, 32, 128);
     if (cfg_c < 0 || cfg_c > 24) cfg_c = 0;
     // Stream priorities (greatest first): the witness map (H's MSM waits for it), then the G2 MSM (longest latency-bound
     // tail: its point additions cost ~3x a G1 addition), then H (starts last), then L / A / B-in-G1.  The heavy
@@ -181,9 +345,11 @@ struct Engine : IEngine {
     auto level = [&](int k) { return std::min(prio_lo, prio_hi + k); };
     for (Slot& sl : slots) {
       G16_CUDA(cudaStreamCreateWithPriority(&sl.st_main, cudaStreamNonBlocking, level(0)));
+      nvtxNameCudaStreamA(sl.st_main, SPAN_WITNESS_MAP);
       for (int i = 0; i < 5; i++) {
         const int pr = i == M_B2 ? level(1) : (i == M_H ? level(2) : prio_lo);
         G16_CUDA(cudaStreamCreateWithPriority(&sl.st_msm[i], cudaStreamNonBlocking, pr));
+        nvtxNameCudaStreamA(sl.st_msm[i], span_of(i));
       }
       G16_CUDA(cudaEventCreate(&sl.ev_start));
       G16_CUDA(cudaEventCreate(&sl.ev_z));
@@ -200,10 +366,12 @@ struct Engine : IEngine {
   ~Engine() override {
     cudaSetDevice(device);
     for (Slot& sl : slots)
-      if (sl.helper.joinable()) sl.helper.join();
-    if (asm_helper.joinable()) asm_helper.join();
+      if (sl.helper) sl.helper->wait();
+    if (asm_helper) asm_helper->wait();
+    pool.reset();
     cudaDeviceSynchronize();
     dom.release();
+    dom_api.release();
     for (Slot& sl : slots) {
       sl.d_z.release(); sl.d_a.release(); sl.d_b.release(); sl.d_c.release(); sl.d_t.release(); sl.d_h.release();
       for (auto& w : sl.ws1) w.release();
@@ -266,13 +434,21 @@ struct Engine : IEngine {
     G16_CUDA(sl.d_t.reserve(bytes)); G16_CUDA(sl.d_h.reserve(bytes));
     return G16_OK;
   }
-  int ensure_domain(int Ln) {
-    if (dom.L != Ln) {
+  int ensure_domain(NttDomain<Fr>& d, int Ln) {
+    if (d.L != Ln) {
       G16_CUDA(cudaDeviceSynchronize());
-      G16_CUDA(ntt_domain_build(dom, Ln, S0.st_main, &ntt_launches));
+      G16_CUDA(ntt_domain_build(d, Ln, S0.st_main, &ntt_launches));
       G16_CUDA(cudaStreamSynchronize(S0.st_main));
     }
     return ensure_slot_buffers(S0, Ln);
+  }
+  // the resident circuit's domain must be the one the prover / setup run with
+  int ensure_circuit_domain() { return ensure_domain(dom, L); }
+  // stand-alone transforms: the circuit's tables when the size matches, a separate domain otherwise
+  NttDomain<Fr>* api_domain(int Ln, int* rc) {
+    NttDomain<Fr>* d = (have_circuit && Ln == L) ? &dom : &dom_api;
+    *rc = ensure_domain(*d, Ln);
+    return d;
   }
 
   // ---- NTT API ----
@@ -282,7 +458,8 @@ struct Engine : IEngine {
     int rc = check_log(log_n);
     if (rc) return rc;
     G16_CUDA(cudaSetDevice(device));
-    if ((rc = ensure_domain((int)log_n))) return rc;
+    const NttDomain<Fr>& dom = *api_domain((int)log_n, &rc);   // shadows the circuit's domain on purpose
+    if (rc) return rc;
     const size_t bytes = (size_t)sizeof(Fr) << log_n;
     Fr* x = S0.d_a.template as<Fr>();
     Fr* y = S0.d_t.template as<Fr>();
@@ -301,7 +478,7 @@ struct Engine : IEngine {
   }
 
   // a, b, c (device, evaluations over the domain) -> S0.d_h (coefficients of h).  r1cs_to_qap.rs:201-232
-  void witness_map_device(Slot& sl) {
+  void witness_map_device(Slot& sl, const NttDomain<Fr>& dom) {
     cudaStream_t st = sl.st_main;
     Fr* A = sl.d_a.template as<Fr>(); Fr* B = sl.d_b.template as<Fr>(); Fr* C = sl.d_c.template as<Fr>(); Fr* T = sl.d_t.template as<Fr>(); Fr* H = sl.d_h.template as<Fr>();
     const Fr zero = Fr::zero();
@@ -321,12 +498,13 @@ struct Engine : IEngine {
     int rc = check_log(log_n);
     if (rc) return rc;
     G16_CUDA(cudaSetDevice(device));
-    if ((rc = ensure_domain((int)log_n))) return rc;
+    const NttDomain<Fr>* d = api_domain((int)log_n, &rc);
+    if (rc) return rc;
     const size_t bytes = (size_t)sizeof(Fr) << log_n;
     G16_CUDA(cudaMemcpyAsync(S0.d_a.p, a, bytes, cudaMemcpyHostToDevice, S0.st_main));
     G16_CUDA(cudaMemcpyAsync(S0.d_b.p, b, bytes, cudaMemcpyHostToDevice, S0.st_main));
     G16_CUDA(cudaMemcpyAsync(S0.d_c.p, c, bytes, cudaMemcpyHostToDevice, S0.st_main));
-    witness_map_device(S0);
+    witness_map_device(S0, *d);
     G16_CUDA(cudaGetLastError());
     G16_CUDA(cudaMemcpyAsync(h, S0.d_h.p, bytes, cudaMemcpyDeviceToHost, S0.st_main));
     G16_CUDA(cudaStreamSynchronize(S0.st_main));
@@ -377,6 +555,9 @@ struct Engine : IEngine {
     const uint32_t nvars = ni + nw;
     for (int m = 0; m < 3; m++) {
       if (!ms[m]->row_ptr) return fail(G16_ERR_BAD_ARGUMENT, "null row_ptr");
+      if (ms[m]->row_ptr[0] != 0) return fail(G16_ERR_BAD_ARGUMENT, "row_ptr[0] must be 0");
+      for (uint32_t i = 0; i < nc; i++)
+        if (ms[m]->row_ptr[i + 1] < ms[m]->row_ptr[i]) return fail(G16_ERR_BAD_ARGUMENT, "row_ptr must be non-decreasing");
       const uint32_t nnz = ms[m]->row_ptr[nc];
       if (nnz && (!ms[m]->col || !ms[m]->val)) return fail(G16_ERR_BAD_ARGUMENT, "null col/val");
       for (uint32_t e = 0; e < nnz; e++) if (ms[m]->col[e] >= nvars) return fail(G16_ERR_BAD_ARGUMENT, "column index out of range");
@@ -395,7 +576,7 @@ struct Engine : IEngine {
     }
     num_inputs = ni; num_constraints = nc; num_witness = nw; L = Ln;
     G16_CUDA(S0.d_z.reserve((size_t)nvars * 32));
-    if ((rc = ensure_domain(L))) return rc;
+    if ((rc = ensure_circuit_domain())) return rc;
     G16_CUDA(cudaStreamSynchronize(S0.st_main));
     have_circuit = true;
     have_pk = false;
@@ -462,6 +643,7 @@ struct Engine : IEngine {
     G16_CUDA(cudaStreamSynchronize(S0.st_main));
     have_pk = true;
     from_setup = false;
+    decide_ba_memory();
     return G16_OK;
   }
 
@@ -482,6 +664,7 @@ struct Engine : IEngine {
     const A1 g1 = load_a1(g1_);
     const A2 g2 = load_a2(g2_);
     if (gamma.is_zero() || delta.is_zero()) return fail(G16_ERR_BAD_ARGUMENT, "gamma/delta must be invertible (UnexpectedIdentity)");
+    { int rc0 = ensure_circuit_domain(); if (rc0) return rc0; }   // dom.omega / dom.n_inv below are the circuit's
     const uint64_t n = 1ull << L;
     const uint32_t nc = num_constraints, ni = num_inputs;
     const uint64_t nv = nvars();
@@ -576,6 +759,7 @@ struct Engine : IEngine {
     d_s.release(); tab1.release(); tab2.release();
     have_pk = true;
     from_setup = true;
+    decide_ba_memory();
     return G16_OK;
   }
   int pk_export(const g16_pk_export_desc* o) override {
@@ -602,8 +786,9 @@ struct Engine : IEngine {
   // enqueue on sl.st_main: upload z, row evaluation, witness map
   int enqueue_witness_map(Slot& sl, const uint64_t* z, uint32_t flags) {
     const uint64_t nv = nvars();
-    int rc = ensure_slot_buffers(sl, L);
+    int rc = ensure_circuit_domain();   // no-op unless something rebuilt `dom` for another size
     if (rc) return rc;
+    if ((rc = ensure_slot_buffers(sl, L))) return rc;
     G16_CUDA(sl.d_z.reserve((size_t)nv * 32));
     sl.tm.h2d_bytes = 0;
     G16_CUDA(cudaEventRecord(sl.ev_start, sl.st_main));
@@ -620,7 +805,7 @@ struct Engine : IEngine {
     r1cs_matvec<Fr>(sl.st_main, cs, sl.d_z.template as<Fr>(), num_constraints, num_inputs, n, sl.d_a.template as<Fr>(),
                     sl.d_b.template as<Fr>(), sl.d_c.template as<Fr>());
     ntt_launches++;
-    witness_map_device(sl);
+    witness_map_device(sl, dom);
     G16_CUDA(cudaGetLastError());
     G16_CUDA(cudaEventRecord(sl.ev_h, sl.st_main));
     return G16_OK;
@@ -644,6 +829,7 @@ struct Engine : IEngine {
     if (!r || !z) return fail(G16_ERR_BAD_ARGUMENT, "null buffer");
     if (sl.busy) return fail(G16_ERR_BAD_ARGUMENT, "slot already has a proof in flight (g16_prove_wait first)");
     G16_CUDA(cudaSetDevice(device));
+    NvtxSpan span_prover(SPAN_PROVER);
     sl.launches0 = ctr.launches + ntt_launches;
     sl.serial = (flags & G16_SERIAL_MSMS) != 0;
     sl.r = load_fr(r);
@@ -651,10 +837,14 @@ struct Engine : IEngine {
     if (s) sl.s = load_fr(s);
     const bool r_zero = sl.r.is_zero();
     if (sl.have_s) {
-      if (sl.helper.joinable()) sl.helper.join();
-      sl.helper = std::thread([this, &sl]() { sl.fx = fixed_muls(sl.r, sl.s); });
+      if (sl.helper) sl.helper->wait();
+      sl.helper = pool->submit([this, &sl]() { sl.fx = fixed_muls(sl.r, sl.s); });
     }
-    int rc = enqueue_witness_map(sl, z, flags);
+    int rc;
+    {
+      NvtxSpan span_wm(SPAN_WITNESS_MAP);
+      rc = enqueue_witness_map(sl, z, flags);
+    }
     if (rc) return rc;
     const uint32_t* zs = sl.d_z.template as<uint32_t>();
     const uint32_t* hs = sl.d_h.template as<uint32_t>();
@@ -669,6 +859,7 @@ struct Engine : IEngine {
     const int order[5] = {M_L, M_A, M_B1, M_B2, M_H};                    // H last: it waits for the witness map
     for (int oi = 0; oi < 5; oi++) {
       const int m = order[oi];
+      NvtxSpan span_msm(span_of(m));
       cudaStream_t st = sl.serial ? sl.st_main : sl.st_msm[m];
       if (!sl.serial) G16_CUDA(cudaStreamWaitEvent(st, m == M_H ? sl.ev_h : sl.ev_z, 0));
       G16_CUDA(cudaEventRecord(sl.ev_m0[m], st));
@@ -696,9 +887,9 @@ struct Engine : IEngine {
     {
       cudaError_t errs[5] = {cudaSuccess, cudaSuccess, cudaSuccess, cudaSuccess, cudaSuccess};
       P1* outs1[4] = {&out.h, &out.l, &out.a, &out.b1};
-      std::thread th[5];
+      std::shared_ptr<HostPool::Ticket> tk[5];
       for (int m = 0; m < 5; m++) {
-        th[m] = std::thread([&, m]() {
+        tk[m] = pool->submit([&, m]() {
           cudaSetDevice(device);
           if (!sl.serial) errs[m] = cudaStreamSynchronize(sl.st_msm[m]);
           if (errs[m] != cudaSuccess) return;
@@ -706,7 +897,7 @@ struct Engine : IEngine {
           else *outs1[m] = sl.run[m] ? msm_finish<Fq>(sl.ws1[m], sl.geom[m]) : P1::inf();
         });
       }
-      for (auto& t : th) t.join();
+      for (auto& t : tk) t->wait();
       for (int m = 0; m < 5; m++)
         if (errs[m] != cudaSuccess) return fail(G16_ERR_CUDA, std::string("msm stream sync: ") + cudaGetErrorString(errs[m]));
       G16_CUDA(cudaStreamSynchronize(sl.st_main));
@@ -720,7 +911,11 @@ struct Engine : IEngine {
     for (int m = 0; m < 5; m++) {
       cudaEventElapsedTime(&sl.tm.msm_ms[m], sl.ev_m0[m], sl.ev_m1[m]);
       sl.tm.msm_accum_ms[m] = 0;
-      if (sl.run[m]) cudaEventElapsedTime(&sl.tm.msm_accum_ms[m], sl.ev_a0[m], sl.ev_a1[m]);
+      sl.tm.msm_entries[m] = 0;
+      if (sl.run[m]) {
+        cudaEventElapsedTime(&sl.tm.msm_accum_ms[m], sl.ev_a0[m], sl.ev_a1[m]);
+        sl.tm.msm_entries[m] = m == M_B2 ? *sl.ws2.h_total : *sl.ws1[m].h_total;
+      }
       cudaEventElapsedTime(&ms, sl.ev_start, sl.ev_m1[m]);
       if (ms > tot) tot = ms;
     }
@@ -776,6 +971,7 @@ struct Engine : IEngine {
     return f;
   }
   int assemble(const Fr& r, const Fr& s, const Partials& x, const FixedMuls& f, uint64_t* proof) {
+    NvtxSpan span_finish(SPAN_FINISH_C);
     uint32_t rk[8], sk[8];
     fr_to_canon(r, rk);
     fr_to_canon(s, sk);
@@ -820,7 +1016,7 @@ struct Engine : IEngine {
     Slot& sl = slots[slot];
     Partials x;
     int rc = wait_partials(sl, x);
-    if (sl.helper.joinable()) sl.helper.join();
+    if (sl.helper) { sl.helper->wait(); sl.helper.reset(); }
     if (rc) return rc;
     if (!sl.have_s) return fail(G16_ERR_BAD_ARGUMENT, "slot holds a partial proof (use g16_prove_partial_wait)");
     auto t0 = std::chrono::steady_clock::now();
@@ -841,21 +1037,21 @@ struct Engine : IEngine {
   Fr asm_r, asm_s;
   FixedMuls asm_fx;
   bool asm_valid = false;
-  std::thread asm_helper;
+  std::shared_ptr<HostPool::Ticket> asm_helper;
   int assemble_prepare(const uint64_t* r, const uint64_t* s) override {
     if (!have_pk) return fail(G16_ERR_BAD_ARGUMENT, "no proving key resident");
     if (!r || !s) return fail(G16_ERR_BAD_ARGUMENT, "null buffer");
-    if (asm_helper.joinable()) asm_helper.join();
+    if (asm_helper) asm_helper->wait();
     asm_r = load_fr(r);
     asm_s = load_fr(s);
     asm_valid = true;
-    asm_helper = std::thread([this]() { asm_fx = fixed_muls(asm_r, asm_s); });
+    asm_helper = pool->submit([this]() { asm_fx = fixed_muls(asm_r, asm_s); });
     return G16_OK;
   }
   int prove_assemble(const uint64_t* r, const uint64_t* s, const uint64_t* partials, uint32_t nparts, uint64_t* proof) override {
     if (!have_pk) return fail(G16_ERR_BAD_ARGUMENT, "no proving key resident");
     if (!r || !s || !partials || !proof || nparts == 0) return fail(G16_ERR_BAD_ARGUMENT, "null buffer");
-    if (asm_helper.joinable()) asm_helper.join();
+    if (asm_helper) { asm_helper->wait(); asm_helper.reset(); }
     Partials x{P1::inf(), P1::inf(), P1::inf(), P1::inf(), P2::inf()};
     const int pl = partial_limbs();
     for (uint32_t i = 0; i < nparts; i++) {   // fixed rank order; the sum is order-independent anyway

@@ -38,6 +38,10 @@ struct MsmGeom {
   uint64_t max_entries;  // n * W
   int k0;            // sorted entries per thread in the level-0 accumulation (64 for large MSMs, less to fill the GPU)
   int ba;            // batched-affine pre-reduction rounds before the accumulation (msm_ba.cuh); 0 = none
+  int ba_m;          // batched-affine: additions per thread and round
+  int ba_G;          // batched-affine: thread products per field inversion
+  int ba_gcd;        // batched-affine: 1 = safegcd inversion, 0 = Fermat
+  int acc_block;     // threads per block of the level-0 accumulation (32 / 64 / 128)
 };
 
 static constexpr int MSM_K0_MAX = 64;
@@ -70,6 +74,10 @@ inline MsmGeom msm_geom(uint64_t n, int scalar_bits, int c_override = 0, int ne_
   g.max_entries = (uint64_t)n * g.W;
   g.k0 = MSM_K0_MAX;
   g.ba = 0;
+  g.ba_m = 16;
+  g.ba_G = 64;
+  g.ba_gcd = 1;
+  g.acc_block = 128;
   return g;
 }
 
@@ -157,13 +165,14 @@ static __device__ __forceinline__ uint32_t block_exclusive_scan_1024(uint32_t v,
   *total = sh[63];
   return warp_off + x - v;
 }
+// pad_mask = 2^R - 1: every bucket is padded to a multiple of 2^R slots (regular layout of the batched-affine rounds)
 static __global__ void __launch_bounds__(1024) msm_scan_blocks(const uint32_t* hist, uint32_t nkeys, uint32_t* offsets,
-                                                               uint32_t* block_tot) {
+                                                               uint32_t* block_tot, uint32_t pad_mask) {
   __shared__ uint32_t sh[64];
   const uint32_t base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
   uint32_t v[SCAN_ITEMS], s = 0;
 #pragma unroll
-  for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = (base + k < nkeys) ? hist[base + k] : 0; s += v[k]; }
+  for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = (base + k < nkeys) ? ((hist[base + k] + pad_mask) & ~pad_mask) : 0; s += v[k]; }
   uint32_t tot;
   uint32_t run = block_exclusive_scan_1024(s, sh, &tot);
 #pragma unroll
@@ -201,8 +210,18 @@ static __global__ void __launch_bounds__(1024) msm_scan_fix(uint32_t* offsets, u
     }
 }
 
+// After the scatter the cursor of bucket b stands at the end of its real entries; the slots from there to the start of
+// the next bucket are padding: marked empty (index) and given the bucket's key.  One thread per bucket, < 2^R writes.
+static __global__ void __launch_bounds__(256) msm_pad_fill(const uint32_t* __restrict__ cursors, const uint32_t* __restrict__ offsets,
+                                                           uint32_t nkeys, uint32_t* __restrict__ sidx, uint32_t* __restrict__ skey) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nkeys) return;
+  const uint32_t end = offsets[b + 1];
+  for (uint32_t p = cursors[b]; p < end; p++) { sidx[p] = MSM_INVALID; skey[p] = b; }
+}
+
 }  // namespace g16
-#include "msm_ba.cuh"   // optional batched-affine pre-reduction (uses block_exclusive_scan_1024)
+#include "msm_ba.cuh"   // batched-affine pre-reduction of the sorted entries
 namespace g16 {
 
 // ------------------------------------------------------------------------------------------------
@@ -256,14 +275,16 @@ struct MsmAccumCfg { static constexpr int MIN_BLOCKS = sizeof(F) <= 48 ? 3 : 2; 
 // coordinates of the gathered base fetched on demand (x, then y) for Fq2 points: 24 fewer live registers at the peak
 template <class F>
 __host__ __device__ constexpr bool msm_lazy_load() { return sizeof(F) > 48; }
+// `sidx` == nullptr: the entries are the points of `bases` themselves (last list of the batched-affine rounds) and the
+// key of entry e is skey[e << key_shift]; empty slots (MSM_INVALID index, or the point (0,0)) add nothing.
 template <class F>
 __global__ void __launch_bounds__(128, MsmAccumCfg<F>::MIN_BLOCKS) msm_accum_l0(const Affine<F>* __restrict__ bases,
                                                     const uint32_t* __restrict__ sidx,
-                                                    const uint32_t* __restrict__ skey,
+                                                    const uint32_t* __restrict__ skey, uint32_t key_shift,
                                                     const uint32_t* __restrict__ total_ptr, uint64_t T0, uint32_t K0,
                                                     XYZZ<F>* __restrict__ buckets, uint32_t* __restrict__ okeys,
                                                     XYZZ<F>* __restrict__ opts, uint32_t* pending0) {
-  const uint32_t M = *total_ptr;
+  const uint32_t M = *total_ptr >> key_shift;
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t == 0) *pending0 = 1;   // level 0 always hands a (possibly empty) partial list to level 1
   if (t >= T0) return;
@@ -271,21 +292,23 @@ __global__ void __launch_bounds__(128, MsmAccumCfg<F>::MIN_BLOCKS) msm_accum_l0(
   const uint64_t begin = t * (uint64_t)K0;
   if (begin >= M) { em.finish(); return; }
   const uint32_t end = (uint32_t)min((uint64_t)M, begin + K0);
-  const uint32_t prev = begin > 0 ? skey[begin - 1] : MSM_INVALID;
-  const uint32_t next = end < M ? skey[end] : MSM_INVALID;
-  uint32_t cur = skey[begin];
+  auto key_at = [&](uint64_t e) { return skey[e << key_shift]; };
+  const uint32_t prev = begin > 0 ? key_at(begin - 1) : MSM_INVALID;
+  const uint32_t next = end < M ? key_at(end) : MSM_INVALID;
+  uint32_t cur = key_at(begin);
   bool first_seg = true;
   XYZZ<F> acc = XYZZ<F>::inf();
 #pragma unroll 1
   for (uint32_t e = (uint32_t)begin; e < end; e++) {
-    const uint32_t k = skey[e];
+    const uint32_t k = key_at(e);
     if (k != cur) {
       em.flush(cur, acc, first_seg && prev == cur, false);
       first_seg = false;
       cur = k;
       acc = XYZZ<F>::inf();
     }
-    const uint32_t ix = sidx[e];
+    const uint32_t ix = sidx ? sidx[e] : e;
+    if (ix == MSM_INVALID) continue;
     if (msm_lazy_load<F>()) {
       const uint4* src = reinterpret_cast<const uint4*>(bases + (ix & 0x7fffffffu));
       constexpr int NVH = sizeof(F) / 16;
@@ -296,10 +319,10 @@ __global__ void __launch_bounds__(128, MsmAccumCfg<F>::MIN_BLOCKS) msm_accum_l0(
         for (int j = 0; j < NVH; j++) d[j] = __ldg(src + half * NVH + j);
         return v;
       };
-      acc.madd_lazy([&]() { return ld(0); }, [&]() { return ld(1); }, (ix >> 31) != 0);
+      acc.madd_lazy([&]() { return ld(0); }, [&]() { return ld(1); }, sidx && (ix >> 31) != 0);
     } else {
       const Affine<F> p = load_affine(bases, ix & 0x7fffffffu);
-      acc.madd_inline(p, (ix >> 31) != 0);
+      acc.madd_inline(p, sidx && (ix >> 31) != 0);
     }
   }
   em.flush(cur, acc, first_seg && prev == cur, next == cur);
@@ -546,22 +569,21 @@ static constexpr int MSM_TAIL_S = 2048;  // partial-list length at which the rem
 // lengths live on the device), outputs per thread of every round and the entries per thread of the accumulation
 // that finishes the last list.
 static constexpr int MSM_BA_MAX_ROUNDS = 6;
-static constexpr uint32_t MSM_BA_G = 64;   // thread products per combine lane = per field inversion
 struct MsmBaPlan {
   int R = 0;
-  uint64_t len[MSM_BA_MAX_ROUNDS + 1] = {0};
+  uint64_t len[MSM_BA_MAX_ROUNDS + 1] = {0};   // len[r] = slots of list r (len[0]: padded sorted slots), upper bounds
   uint32_t m[MSM_BA_MAX_ROUNDS] = {0};
   uint64_t threads_max = 0;
   int k0_final = 0;
   void make(const MsmGeom& g) {
     R = g.ba < 0 ? 0 : (g.ba > MSM_BA_MAX_ROUNDS ? MSM_BA_MAX_ROUNDS : g.ba);
-    len[0] = g.max_entries;
+    // every bucket is padded to a multiple of 2^R slots: at most 2^R - 1 extra slots per bucket
+    len[0] = R > 0 ? ((g.max_entries + (uint64_t)g.nkeys * ((1u << R) - 1)) >> R) << R : g.max_entries;
     threads_max = 0;
     for (int r = 0; r < R; r++) {
-      len[r + 1] = ba_next_max(len[r], g.nkeys);
-      static const uint32_t m_max = [] { const char* e = getenv("G16_BA_M"); const int v = e ? atoi(e) : 32; return (uint32_t)((v >= 1 && v <= 256) ? v : 32); }();
-      uint32_t mm = m_max;
-      while (mm > 4 && len[r + 1] / mm < 200000) mm >>= 1;
+      len[r + 1] = len[r] >> 1;
+      uint32_t mm = (uint32_t)(g.ba_m < 1 ? 1 : g.ba_m);
+      while (mm > 4 && len[r + 1] / mm < 200000) mm >>= 1;   // keep at least ~200k threads per round
       m[r] = mm;
       const uint64_t T = ba_threads(len[r + 1], mm);
       if (T > threads_max) threads_max = T;
@@ -573,17 +595,24 @@ struct MsmBaPlan {
   uint64_t l0_threads(const MsmGeom& g) const {
     return R > 0 ? (len[R] + k0_final - 1) / k0_final : (g.max_entries + g.k0 - 1) / g.k0;
   }
+  // device bytes the rounds need on top of the plain pipeline (per MSM and proof slot)
+  template <class F>
+  uint64_t extra_bytes() const {
+    if (R == 0) return 0;
+    return len[1] * (sizeof(F) + sizeof(Affine<F>)) + (R > 1 ? len[2] * sizeof(Affine<F>) : 0) + 2 * threads_max * sizeof(F);
+  }
 };
 
 template <class F>
 struct MsmWorkspace {
   DevBuf counters, offsets, blocktot, sidx, skey, buckets, pk0, pp0, pk1, pp1, pending, red_inner, red_leaf;
-  DevBuf ba_off, ba_pre, ba_key, ba_ident, ba_prod, ba_pre2, ba_l0, ba_l1;
+  DevBuf ba_pre, ba_prod, ba_pre2, ba_l0, ba_l1;
   MsmBaPlan bap;
   MsmRedPlan plan;
   int plan_m = -1, plan_ne = 0;
   XYZZ<F>* h_leaf = nullptr;  // pinned host copy of the leaf arrays: [node][window][element]
   size_t h_cap = 0;
+  uint32_t* h_total = nullptr;  // pinned: number of sorted slots of the last MSM (entries + bucket padding)
   cudaError_t prepare(const MsmGeom& g) {
     cudaError_t e;
     bap.make(g);
@@ -593,10 +622,7 @@ struct MsmWorkspace {
     const uint64_t S2 = 2 * T1;
 #define G16_TRY(x) if ((e = (x)) != cudaSuccess) return e
     if (bap.R > 0) {
-      G16_TRY(ba_off.reserve((size_t)(bap.R + 1) * (g.nkeys + 1) * 4));
       G16_TRY(ba_pre.reserve(bap.len[1] * sizeof(F) + 16));
-      G16_TRY(ba_key.reserve(bap.len[1] * 4 + 16));
-      G16_TRY(ba_ident.reserve(bap.len[1] * 4 + 16));
       G16_TRY(ba_prod.reserve(bap.threads_max * sizeof(F) + 16));
       G16_TRY(ba_pre2.reserve(bap.threads_max * sizeof(F) + 16));
       G16_TRY(ba_l0.reserve(bap.len[1] * sizeof(Affine<F>) + 16));
@@ -605,8 +631,8 @@ struct MsmWorkspace {
     G16_TRY(counters.reserve((size_t)(g.nkeys + 1) * 4));
     G16_TRY(offsets.reserve((size_t)(g.nkeys + 1) * 4));
     G16_TRY(blocktot.reserve((size_t)((g.nkeys + SCAN_BLOCK - 1) / SCAN_BLOCK + 1) * 4));
-    G16_TRY(sidx.reserve(g.max_entries * 4 + 16));
-    G16_TRY(skey.reserve(g.max_entries * 4 + 16));
+    G16_TRY(sidx.reserve(bap.len[0] * 4 + 16));
+    G16_TRY(skey.reserve(bap.len[0] * 4 + 16));
     G16_TRY(buckets.reserve((size_t)g.nkeys * sizeof(XYZZ<F>)));
     G16_TRY(pk0.reserve(S1 * 4 + 16));
     G16_TRY(pp0.reserve(S1 * sizeof(XYZZ<F>)));
@@ -620,6 +646,7 @@ struct MsmWorkspace {
     }
     G16_TRY(red_inner.reserve((plan.inner_pts * g.ne + 1) * sizeof(XYZZ<F>)));
     G16_TRY(red_leaf.reserve((plan.leaf_pts * g.ne + 1) * sizeof(XYZZ<F>)));
+    if (!h_total) G16_TRY(cudaMallocHost(&h_total, 16));
     const size_t need = plan.leaf_pts * g.ne;
     if (h_cap < need) {
       if (h_leaf) cudaFreeHost(h_leaf);
@@ -633,10 +660,12 @@ struct MsmWorkspace {
   void release() {
     counters.release(); offsets.release(); blocktot.release(); sidx.release(); skey.release(); buckets.release();
     pk0.release(); pp0.release(); pk1.release(); pp1.release(); pending.release(); red_inner.release(); red_leaf.release();
-    ba_off.release(); ba_pre.release(); ba_key.release(); ba_ident.release(); ba_prod.release(); ba_pre2.release();
+    ba_pre.release(); ba_prod.release(); ba_pre2.release();
     ba_l0.release(); ba_l1.release();
     if (h_leaf) cudaFreeHost(h_leaf);
+    if (h_total) cudaFreeHost(h_total);
     h_leaf = nullptr;
+    h_total = nullptr;
     h_cap = 0;
   }
 };
@@ -667,52 +696,44 @@ cudaError_t msm_enqueue(cudaStream_t st, MsmWorkspace<F>& ws, const MsmGeom& g, 
   cudaMemsetAsync(buckets, 0, (size_t)g.nkeys * sizeof(XYZZ<F>), st);
   const uint32_t nb = (g.n + 255) / 256;
   msm_digits<FrF, false><<<nb, 256, 0, st>>>(d_scalars, scalar_stride, scalars_mont ? 1 : 0, d_skip, g, counters, nullptr, nullptr);
+  const MsmBaPlan& bp = ws.bap;
+  const uint32_t pad_mask = bp.R > 0 ? (1u << bp.R) - 1 : 0;
   const uint32_t sb = (g.nkeys + SCAN_BLOCK - 1) / SCAN_BLOCK;
-  msm_scan_blocks<<<sb, 1024, 0, st>>>(counters, g.nkeys, offsets, blocktot);
+  msm_scan_blocks<<<sb, 1024, 0, st>>>(counters, g.nkeys, offsets, blocktot, pad_mask);
   msm_scan_tops<<<1, 1024, 0, st>>>(blocktot, sb, offsets + g.nkeys);
   msm_scan_fix<<<sb, 1024, 0, st>>>(offsets, g.nkeys, blocktot, counters);
   msm_digits<FrF, true><<<nb, 256, 0, st>>>(d_scalars, scalar_stride, scalars_mont ? 1 : 0, d_skip, g, counters, sidx, skey);
   nl += 5;
-  // optional batched-affine rounds: the sorted entries shrink to a list of partial bucket sums (msm_ba.cuh)
-  const MsmBaPlan& bp = ws.bap;
+  // batched-affine rounds: the (padded) sorted slots shrink 2^R-fold to a list of partial bucket sums (msm_ba.cuh)
   const Affine<F>* acc_bases = d_bases;
-  const uint32_t *acc_sidx = sidx, *acc_skey = skey, *acc_total = offsets + g.nkeys;
+  const uint32_t* acc_sidx = sidx;
+  const uint32_t* total0 = offsets + g.nkeys;
   if (ev_acc0) cudaEventRecord(ev_acc0, st);
   if (bp.R > 0) {
-    uint32_t* ba_off = ws.ba_off.template as<uint32_t>();
-    Affine<F>* lists[2] = {ws.ba_l0.template as<Affine<F>>(), ws.ba_l1.template as<Affine<F>>()};
-    static const uint32_t ba_G = [] { const char* e = getenv("G16_BA_G"); const int v = e ? atoi(e) : (int)MSM_BA_G; return (uint32_t)((v >= 1 && v <= 4096) ? v : (int)MSM_BA_G); }();
-    static const bool ba_lean = [] { const char* e = getenv("G16_BA_LEAN"); return e && atoi(e) > 0; }();
-    static const uint32_t ba_gcd = [] { const char* e = getenv("G16_BA_INV_GCD"); return (uint32_t)(e && atoi(e) > 0); }();
-    ba_offsets_kernel<<<1, 1024, 0, st>>>(offsets, g.nkeys, bp.R, ba_off);
+    msm_pad_fill<<<(g.nkeys + 255) / 256, 256, 0, st>>>(counters, offsets, g.nkeys, sidx, skey);
     nl += 1;
+    Affine<F>* lists[2] = {ws.ba_l0.template as<Affine<F>>(), ws.ba_l1.template as<Affine<F>>()};
     for (int r = 0; r < bp.R; r++) {
       BaRound<F> a;
       a.in = r == 0 ? d_bases : lists[(r - 1) & 1];
       a.sidx = r == 0 ? sidx : nullptr;
-      a.off_in = ba_off + (size_t)r * (g.nkeys + 1);
-      a.off_out = ba_off + (size_t)(r + 1) * (g.nkeys + 1);
-      a.nkeys = g.nkeys;
+      a.total0 = total0;
+      a.shift = (uint32_t)(r + 1);
       a.m = bp.m[r];
-      a.G = ba_G;
-      a.inv_gcd = ba_gcd;
+      a.G = (uint32_t)(g.ba_G < 1 ? 1 : g.ba_G);
+      a.inv_gcd = (uint32_t)g.ba_gcd;
       a.pre = ws.ba_pre.template as<F>();
-      a.key = ws.ba_key.template as<uint32_t>();
-      a.ident = ws.ba_ident.template as<uint32_t>();
       a.prod = ws.ba_prod.template as<F>();
       a.pre2 = ws.ba_pre2.template as<F>();
       a.out = lists[r & 1];
       const uint64_t T = ba_threads(bp.len[r + 1], a.m), lanes = (T + a.G - 1) / a.G;
       ba_forward_kernel<F><<<(unsigned)((T + 127) / 128), 128, 0, st>>>(a);
       ba_combine_kernel<F><<<(unsigned)((lanes + 31) / 32), 32, 0, st>>>(a);
-      if (ba_lean) ba_backward_lean_kernel<F><<<(unsigned)((T + 127) / 128), 128, 0, st>>>(a);
-      else ba_backward_kernel<F><<<(unsigned)((T + 127) / 128), 128, 0, st>>>(a);
+      ba_backward_kernel<F><<<(unsigned)((T + 127) / 128), 128, 0, st>>>(a);
       nl += 3;
     }
     acc_bases = lists[(bp.R - 1) & 1];
-    acc_sidx = ws.ba_ident.template as<uint32_t>();
-    acc_skey = ws.ba_key.template as<uint32_t>();
-    acc_total = ba_off + (size_t)bp.R * (g.nkeys + 1) + g.nkeys;
+    acc_sidx = nullptr;
   }
   // level 0
   const uint64_t T0 = bp.l0_threads(g);
@@ -720,8 +741,8 @@ cudaError_t msm_enqueue(cudaStream_t st, MsmWorkspace<F>& ws, const MsmGeom& g, 
   uint32_t* kk[2] = {ws.pk0.template as<uint32_t>(), ws.pk1.template as<uint32_t>()};
   XYZZ<F>* pp[2] = {ws.pp0.template as<XYZZ<F>>(), ws.pp1.template as<XYZZ<F>>()};
   {
-    static const unsigned tpb = [] { const char* e = getenv("G16_ACC_BLOCK"); int v = e ? atoi(e) : 128; return (unsigned)((v == 32 || v == 64) ? v : 128); }();
-    msm_accum_l0<F><<<(unsigned)((T0 + tpb - 1) / tpb), tpb, 0, st>>>(acc_bases, acc_sidx, acc_skey, acc_total, T0, K0, buckets, kk[0], pp[0], pending);
+    const unsigned tpb = (g.acc_block == 32 || g.acc_block == 64) ? (unsigned)g.acc_block : 128u;
+    msm_accum_l0<F><<<(unsigned)((T0 + tpb - 1) / tpb), tpb, 0, st>>>(acc_bases, acc_sidx, skey, (uint32_t)bp.R, total0, T0, K0, buckets, kk[0], pp[0], pending);
   }
   if (ev_acc1) cudaEventRecord(ev_acc1, st);
   nl += 1;
@@ -798,6 +819,7 @@ cudaError_t msm_enqueue(cudaStream_t st, MsmWorkspace<F>& ws, const MsmGeom& g, 
   }
   if (ctr) ctr->launches += nl;
   const XYZZ<F>* leaf_src = pl.nodes[0].leaf ? buckets : leaf;
+  cudaMemcpyAsync(ws.h_total, total0, 4, cudaMemcpyDeviceToHost, st);
   e = cudaMemcpyAsync(ws.h_leaf, leaf_src, pl.leaf_pts * g.ne * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, st);
   if (e != cudaSuccess) return e;
   return cudaGetLastError();

@@ -165,10 +165,29 @@ typedef struct {
   float msm_accum_ms[5]; /* the bucket-accumulation kernel (msm_accum_l0) of each MSM                             */
   float host_finish_ms;  /* host Horner + final assembly (prover.rs:76-131)                                       */
   uint64_t msm_pairs[5]; /* (scalar, base) pairs fed to each MSM on this rank                                     */
+  uint64_t msm_entries[5]; /* sorted bucket slots of each MSM: non-zero signed digits of live pairs (+ bucket padding
+                              of the batched-affine rounds, < 2 %) = point additions of the accumulation stage     */
   uint64_t launches;     /* kernels launched by the last call                                                     */
   uint64_t h2d_bytes, d2h_bytes;
 } g16_timings;
 int g16_get_timings(const g16_ctx* ctx, g16_timings* out);
+
+/* ---- tuning (no counterpart in the reference: ark-ec picks its window size internally) ---------------------------
+ * Launch geometry of the MSM pipeline for the resident key (H query for the G1 fields, B-in-G2 for the G2 ones). */
+typedef struct {
+  int32_t c, ne, copies;              /* window bits, bucket sets, precomputed multiples per base                 */
+  int32_t k0_g1, k0_g2;               /* sorted entries per thread of the level-0 accumulation                    */
+  int32_t ba_rounds_g1, ba_rounds_g2; /* batched-affine rounds before the XYZZ accumulation (0 = none)            */
+  int32_t ba_m, ba_g, ba_inv_gcd;     /* additions per thread and round; products per inversion; 1 = safegcd      */
+  int32_t acc_block, sm_count;
+  int32_t rank, world;
+  int32_t reserved[4];
+} g16_config;
+int g16_get_config(const g16_ctx* ctx, g16_config* out);
+/* key: "msm_ba", "msm_ba_g2", "ba_m", "ba_g", "ba_inv_gcd", "acc_k0_g1", "acc_k0_g2", "acc_block" (the G16_* environment
+ * variables of INTEGRATION.md section 6, read once at g16_ctx_create, in lower case without the prefix).  Takes effect
+ * from the next proof; results never depend on these knobs. */
+int g16_set_option(g16_ctx* ctx, const char* key, int64_t value);
 uint32_t g16_domain_log(const g16_ctx* ctx); /* log2 of the resident circuit's domain size */
 
 #ifdef __cplusplus

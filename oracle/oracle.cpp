@@ -15,6 +15,8 @@
 //   orc_witness_map            r1cs_to_qap.rs:172-235 (evaluate_constraint :28-67, iFFT/coset FFT/pointwise/coset iFFT)
 //   orc_msm_g1 / orc_msm_g2    VariableBaseMSM::msm_bigint as called at prover.rs:66,74,262
 //   orc_prove                  prover.rs:26-51 + :54-132 (+ calculate_coeff :252-270)
+//   orc_setup_scalars          generator.rs:47-127 + r1cs_to_qap.rs:128-170,237-247 (exponents of every key element);
+//                              with orc_batch_mul_g1/g2 (generator.rs:129-183) this is a complete CPU trusted setup
 // Parallelism: every MSM is split into one chunk of (scalar, base) pairs per thread, each chunk a complete serial
 // Pippenger, partial results summed -- this scales to all host cores (ark-ec parallelises at least across windows;
 // chunking is the stronger CPU variant, used here so that the baseline is not handicapped on many-core hosts).
@@ -366,9 +368,62 @@ static Jac<F> pippenger_serial(const Aff<F>* bases, const u64* scalars /* 4 limb
   }
   return total;
 }
+// ark-ec 0.5.0 `msm_bigint` parallelises ACROSS WINDOWS (`ark_std::cfg_into_iter!(window_starts)`: every window walks
+// all n pairs serially, window sums are combined at the end), so its speed-up saturates at W = ceil(256 / c) threads.
+// Kept selectable (orc_set_msm_mode(1)) so that bench.py can print both CPU variants side by side; the default stays
+// the chunk-parallel one below, which is the stronger baseline on many-core hosts.
+static std::atomic<int> g_msm_mode(0);   // 0 = chunk-parallel (default), 1 = window-parallel (ark-ec's scheme)
+template <class F>
+static Jac<F> msm_window_parallel(const Aff<F>* bases, const u64* scalars, size_t n, int bits, int threads) {
+  if (n == 0) return Jac<F>::inf();
+  const int c = ark_window(n);
+  const int W = (bits + 1 + c - 1) / c;
+  const size_t B = (size_t)1 << (c - 1);
+  std::vector<int32_t> digits(n * W);
+  const size_t grain = 1 << 14, tasks = (n + grain - 1) / grain;
+  parallel_for(tasks, threads, [&](size_t t) {
+    for (size_t i = t * grain; i < std::min(n, (t + 1) * grain); i++) {
+      const u64* s = scalars + 4 * i;
+      u64 carry = 0;
+      for (int w = 0; w < W; w++) {
+        int bit = w * c, li = bit / 64, sh = bit % 64;
+        u64 raw = 0;
+        if (li < 4) {
+          raw = s[li] >> sh;
+          if (sh + c > 64 && li + 1 < 4) raw |= s[li + 1] << (64 - sh);
+          raw &= ((u64)1 << c) - 1;
+        }
+        raw += carry;
+        carry = 0;
+        int32_t d = (int32_t)raw;
+        if (raw > B) { d = (int32_t)raw - (int32_t)((u64)1 << c); carry = 1; }
+        digits[i * W + w] = d;
+      }
+    }
+  });
+  std::vector<Jac<F>> wsum(W);
+  parallel_for((size_t)W, threads, [&](size_t w) {
+    std::vector<Jac<F>> buckets(B, Jac<F>::inf());
+    for (size_t i = 0; i < n; i++) {
+      int32_t d = digits[i * W + w];
+      if (d > 0) buckets[d - 1].madd(bases[i], false);
+      else if (d < 0) buckets[-d - 1].madd(bases[i], true);
+    }
+    Jac<F> running = Jac<F>::inf(), sum = Jac<F>::inf();
+    for (size_t b = B; b-- > 0;) { running.add(buckets[b]); sum.add(running); }
+    wsum[w] = sum;
+  });
+  Jac<F> total = Jac<F>::inf();
+  for (int w = W - 1; w >= 0; w--) {
+    for (int k = 0; k < c; k++) total.dbl();
+    total.add(wsum[w]);
+  }
+  return total;
+}
 template <class F>
 static Jac<F> msm_parallel(const Aff<F>* bases, const u64* scalars, size_t n, int bits, int threads) {
   if (n == 0) return Jac<F>::inf();
+  if (g_msm_mode.load() == 1) return msm_window_parallel<F>(bases, scalars, n, bits, threads);
   size_t chunks = std::max<size_t>(1, std::min<size_t>((size_t)threads, n / 1024 + 1));
   std::vector<Jac<F>> part(chunks);
   parallel_for(chunks, threads, [&](size_t t) {
@@ -559,6 +614,69 @@ struct Curve {
     memcpy(h_out, a.data(), d.n * sizeof(Fr));
     return 0;
   }
+  // Exponents of the proving / verifying key from explicit toxic waste: generator.rs:47-127 with
+  // R1CSToQAP::instance_map_with_evaluation (r1cs_to_qap.rs:128-170) and h_query_scalars (:237-247).
+  //   qa[i] = a_i(tau), qb[i] = b_i(tau)                      i < ni + nw      (a_query / b_g1_query / b_g2_query exponents)
+  //   gabc[i] = (beta a_i + alpha b_i + c_i)(tau) / gamma      i < ni           (generator.rs:113-117)
+  //   lq[i]   = (beta a_i + alpha b_i + c_i)(tau) / delta      ni <= i          (generator.rs:119-123)
+  //   hs[i]   = tau^i Z(tau) / delta                           i < n - 1        (generator.rs:168 via :237-247)
+  // All Montgomery Fr.  Returns 1 for PolynomialDegreeTooLarge, 2 when gamma/delta/Z(tau) is not invertible.
+  static int setup_scalars(uint32_t ni, uint32_t nc, uint32_t nw, const Csr* A, const Csr* B, const Csr* C, const u64* toxic /* alpha,beta,gamma,delta,tau */,
+                           u64* qa_, u64* qb_, u64* lq_, u64* hs_, u64* gabc_, int threads) {
+    size_t need = (size_t)nc + ni;
+    int L = 0;
+    while (((size_t)1 << L) < need) L++;
+    if (L > TWO_ADICITY) return 1;
+    const Domain<Fr>& d = cached_domain(L, threads);
+    const Fr* tx = reinterpret_cast<const Fr*>(toxic);
+    const Fr alpha = tx[0], beta = tx[1], gamma = tx[2], delta = tx[3], tau = tx[4];
+    if (gamma.is_zero() || delta.is_zero()) return 2;
+    Fr tn = tau;
+    for (int i = 0; i < L; i++) tn = Fr::sqr(tn);
+    const Fr zt = Fr::sub(tn, Fr::one());            // domain.evaluate_vanishing_polynomial(t), r1cs_to_qap.rs:143
+    if (zt.is_zero()) return 2;                       // tau inside the domain: the reference's sampling never hits it
+    // evaluate_all_lagrange_coefficients(t): u_i = Z(t) w^i / (n (t - w^i)), one batch inversion per chunk of the domain
+    const size_t n = d.n, nv = (size_t)ni + nw;
+    std::vector<Fr> u(n);
+    const Fr zn = Fr::mul(zt, d.n_inv);
+    {
+      const size_t grain = 1 << 12, tasks = (n + grain - 1) / grain;
+      parallel_for(tasks, threads, [&](size_t t) {
+        const size_t lo = t * grain, hi = std::min(n, lo + grain);
+        u64 e[1] = {(u64)lo};
+        Fr w = Fr::pow(d.omega, e, 1);
+        std::vector<Fr> den(hi - lo), pref(hi - lo), ws(hi - lo);
+        Fr acc = Fr::one();
+        for (size_t i = lo; i < hi; i++) { ws[i - lo] = w; den[i - lo] = Fr::sub(tau, w); pref[i - lo] = acc; acc = Fr::mul(acc, den[i - lo]); w = Fr::mul(w, d.omega); }
+        Fr ai = Fr::inv(acc);
+        for (size_t k = hi - lo; k-- > 0;) { Fr di = Fr::mul(ai, pref[k]); ai = Fr::mul(ai, den[k]); u[lo + k] = Fr::mul(Fr::mul(zn, ws[k]), di); }
+      });
+    }
+    std::vector<Fr> qa(nv, Fr::zero()), qb(nv, Fr::zero()), qc(nv, Fr::zero());
+    for (uint32_t i = 0; i < ni; i++) qa[i] = u[nc + i];                                 // r1cs_to_qap.rs:150-155
+    const Csr* ms[3] = {A, B, C};
+    std::vector<Fr>* outs[3] = {&qa, &qb, &qc};
+    parallel_for(3, threads, [&](size_t m) {                                             // r1cs_to_qap.rs:157-167 (scatter: serial per matrix)
+      const Fr* vals = reinterpret_cast<const Fr*>(ms[m]->val);
+      for (uint32_t i = 0; i < nc; i++)
+        for (uint32_t e = ms[m]->row_ptr[i]; e < ms[m]->row_ptr[i + 1]; e++) {
+          Fr& dst = (*outs[m])[ms[m]->col[e]];
+          dst = Fr::add(dst, Fr::mul(u[i], vals[e]));
+        }
+    });
+    const Fr gi = Fr::inv(gamma), di = Fr::inv(delta);
+    Fr* qa_o = reinterpret_cast<Fr*>(qa_); Fr* qb_o = reinterpret_cast<Fr*>(qb_); Fr* lq = reinterpret_cast<Fr*>(lq_);
+    Fr* hs = reinterpret_cast<Fr*>(hs_); Fr* gabc = reinterpret_cast<Fr*>(gabc_);
+    for (size_t i = 0; i < nv; i++) {
+      const Fr t = Fr::add(Fr::add(Fr::mul(beta, qa[i]), Fr::mul(alpha, qb[i])), qc[i]);
+      if (i < ni) gabc[i] = Fr::mul(t, gi); else lq[i - ni] = Fr::mul(t, di);
+      qa_o[i] = qa[i];
+      qb_o[i] = qb[i];
+    }
+    Fr p = Fr::mul(zt, di);
+    for (size_t i = 0; i + 1 < n; i++) { hs[i] = p; p = Fr::mul(p, tau); }
+    return 0;
+  }
   static void to_bigints(const Fr* in, size_t n, std::vector<u64>& out, int threads) {
     out.resize(n * 4);
     const size_t grain = 8192, tasks = (n + grain - 1) / grain;
@@ -723,6 +841,12 @@ int orc_batch_mul_g2(int curve, const u64* g, const u64* scalars, u64 n, u64* ou
     batch_mul<Fq2, Fr>(*reinterpret_cast<const A2*>(g), reinterpret_cast<const Fr*>(scalars), n, reinterpret_cast<A2*>(out), threads);
     return 0;
   })
+}
+int orc_set_msm_mode(int mode) { int old = g_msm_mode.exchange(mode == 1 ? 1 : 0); return old; }
+int orc_setup_scalars(int curve, uint32_t ni, uint32_t nc, uint32_t nw, const Csr* a, const Csr* b, const Csr* c, const u64* toxic,
+                      u64* qa, u64* qb, u64* lq, u64* hs, u64* gabc, int threads) {
+  init_all();
+  DISPATCH(curve, { return C::setup_scalars(ni, nc, nw, a, b, c, toxic, qa, qb, lq, hs, gabc, threads); })
 }
 int orc_prove(int curve, const PkDesc* pk, uint32_t ni, uint32_t nc, uint32_t nw, const Csr* a, const Csr* b, const Csr* c, const u64* z,
               const u64* r, const u64* s, u64* proof, int threads, double* t_ms) {

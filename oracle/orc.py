@@ -152,3 +152,45 @@ def batch_mul_g2(cid, nq, g, scalars, threads=1):
     rc = lib().orc_batch_mul_g2(cid, _p(g), _p(scalars), C.c_uint64(scalars.shape[0]), _p(out), threads)
     assert rc == 0
     return out
+
+
+def set_msm_mode(mode: int) -> int:
+    """0 = chunk-parallel Pippenger (default, the stronger CPU baseline), 1 = ark-ec's window-parallel scheme.  Returns the
+    previous mode."""
+    return lib().orc_set_msm_mode(int(mode))
+
+
+def setup_scalars(cid, m, toxic, threads=1):
+    """Exponents of every proving-key element (generator.rs:47-127, r1cs_to_qap.rs:128-170,237-247).
+    m: ConstraintMatrices-like; toxic: (5, 4) Montgomery limbs alpha, beta, gamma, delta, tau.
+    Returns dict(a, b, l, h, gamma_abc) of Montgomery Fr limb arrays."""
+    keep = []
+    a, b, c = (_csr(t, keep) for t in (m.a, m.b, m.c))
+    ni, nc, nw = m.num_instance_variables, m.num_constraints, m.num_witness_variables
+    n = 1 << max(nc + ni - 1, 0).bit_length()
+    tx = np.ascontiguousarray(toxic, dtype=np.uint64).reshape(5, 4)
+    z = lambda k: np.zeros((k, 4), dtype=np.uint64)
+    out = dict(a=z(ni + nw), b=z(ni + nw), l=z(nw), h=z(n - 1), gamma_abc=z(ni))
+    rc = lib().orc_setup_scalars(cid, ni, nc, nw, C.byref(a), C.byref(b), C.byref(c), _p(tx), _p(out["a"]), _p(out["b"]),
+                                 _p(out["l"]), _p(out["h"]), _p(out["gamma_abc"]), threads)
+    if rc == 1:
+        raise ValueError("PolynomialDegreeTooLarge")
+    assert rc == 0, f"orc_setup_scalars rc={rc}"
+    return out
+
+
+def generate_parameters(cid, nq, m, toxic, g1, g2, threads=1):
+    """Complete CPU trusted setup with explicit toxic waste (generator.rs:47-208): exponents from setup_scalars, every
+    group element by the fixed-base routine (generator.rs:129-183).  toxic: (5,4) Montgomery limbs; g1 / g2: ABI affine
+    generators.  Returns a dict with the ABI arrays of ProvingKey / VerifyingKey (the caller wraps them; this module
+    must not import the product package)."""
+    ex = setup_scalars(cid, m, toxic, threads)
+    tx = np.ascontiguousarray(toxic, dtype=np.uint64).reshape(5, 4)
+    single1 = batch_mul_g1(cid, nq, g1, tx[[0, 1, 3]], threads)          # alpha_g1, beta_g1, delta_g1
+    single2 = batch_mul_g2(cid, nq, g2, tx[[1, 2, 3]], threads)          # beta_g2, gamma_g2, delta_g2
+    return dict(a_query=batch_mul_g1(cid, nq, g1, ex["a"], threads), b_g1_query=batch_mul_g1(cid, nq, g1, ex["b"], threads),
+                b_g2_query=batch_mul_g2(cid, nq, g2, ex["b"], threads), h_query=batch_mul_g1(cid, nq, g1, ex["h"], threads),
+                l_query=batch_mul_g1(cid, nq, g1, ex["l"], threads),
+                gamma_abc_g1=batch_mul_g1(cid, nq, g1, ex["gamma_abc"], threads),
+                alpha_g1=single1[0], beta_g1=single1[1], delta_g1=single1[2],
+                beta_g2=single2[0], gamma_g2=single2[1], delta_g2=single2[2], exponents=ex)

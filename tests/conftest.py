@@ -20,10 +20,14 @@ def _ensure_built():
     lib = os.path.join(ROOT, "groth16_b200", "libg16b200.so")
     orc = os.path.join(ROOT, "oracle", "liboracle.so")
     jobs = str(max(1, min(16, os.cpu_count() or 1)))
-    if not os.path.exists(orc):
-        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-j", jobs])
-    if not os.path.exists(lib):
-        subprocess.check_call(["make", "-C", os.path.join(ROOT, "groth16_b200", "csrc"), "-j", jobs])
+    # `make` is the staleness check: it rebuilds when any source / header (tracked through the -MMD dependency files) is
+    # newer than the library, and is a no-op otherwise -- a stale .so is never tested silently.  On a box without nvcc / g++
+    # in PATH (never the case in this image) the prebuilt libraries are used as shipped.
+    import shutil
+    if shutil.which("g++") or not os.path.exists(orc):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "-j", jobs])
+    if shutil.which("nvcc") or not os.path.exists(lib):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "groth16_b200", "csrc"), "-j", jobs])
 
 
 _ensure_built()

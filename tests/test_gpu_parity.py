@@ -307,16 +307,33 @@ def test_msm_skewed_scalars_large():
     _skewed_msm_check()
 
 
-@pytest.mark.parametrize("rounds", [1, 3])
-def test_batched_affine_rounds(monkeypatch, rounds):
-    """The experimental batched-affine pre-reduction (csrc/msm_ba.cuh, G16_MSM_BA / G16_MSM_BA_G2 = rounds) must not
-    change a single bit: skewed G1 MSM with repeated bases, a 2^14-point G2 MSM, and full proofs (synthetic 2^14, and the
-    degenerate DummyCircuit where every scalar is equal) against the CPU oracle."""
+def _set_ba(rounds_g1, rounds_g2, **kw):
+    for name in ALL_CURVES:
+        g = engine(name)
+        g.set_option("msm_ba", rounds_g1)
+        g.set_option("msm_ba_g2", rounds_g2)
+        for k, v in kw.items():
+            g.set_option(k, v)
+
+
+@pytest.mark.parametrize("rounds,m,G,gcd", [(0, 16, 64, 1), (1, 4, 7, 0), (3, 32, 64, 1), (6, 16, 64, 1)])
+def test_batched_affine_rounds(rounds, m, G, gcd):
+    """The batched-affine pre-reduction (csrc/msm_ba.cuh; default: 4 rounds on G1 MSMs; g16_set_option "msm_ba" /
+    "msm_ba_g2") must not change a single bit whatever the number of rounds (0 = plain XYZZ accumulation), the additions
+    per thread, the products per inversion or the inversion routine: skewed G1 MSM with repeated bases, a 2^14-point G2
+    MSM, and full proofs (synthetic 2^14, and the degenerate DummyCircuit where every scalar is equal) against the CPU
+    oracle."""
     import orc
     from groth16_b200.params import GENERATORS
     from groth16_b200.workload import dummy_r1cs, synthetic_r1cs
-    monkeypatch.setenv("G16_MSM_BA", str(rounds))
-    monkeypatch.setenv("G16_MSM_BA_G2", str(rounds))
+    try:
+        _set_ba(rounds, rounds, ba_m=m, ba_g=G, ba_inv_gcd=gcd)
+        _ba_body(orc, GENERATORS, dummy_r1cs, synthetic_r1cs)
+    finally:
+        _set_ba(4, 0, ba_m=16, ba_g=64, ba_inv_gcd=1)
+
+
+def _ba_body(orc, GENERATORS, dummy_r1cs, synthetic_r1cs):
     _skewed_msm_check()
     curve = "bn254"
     c = P.CURVES[curve]

@@ -168,3 +168,46 @@ def test_oracle_batch_mul(curve):
     g2 = cd.enc_g2([cx.g2_gen()])[0]
     assert cd.dec_g1(orc.batch_mul_g1(c.cid, cd.nq, g1, cd.fr.enc(sc), threads=2)) == [cx.G1.mul(cx.g1_gen(), k) for k in sc]
     assert cd.dec_g2(orc.batch_mul_g2(c.cid, cd.nq, g2, cd.fr.enc(sc), threads=2)) == [cx.G2.mul(cx.g2_gen(), k) for k in sc]
+
+
+@pytest.mark.parametrize("curve", ALL_CURVES)
+def test_oracle_setup_matches_pyref(curve):
+    """orc.generate_parameters (generator.rs:47-208 restated in C++) against the big-int setup of pyref: every exponent and
+    every key element, then a proof under that key verifies with the pairing."""
+    from util import oracle_setup
+    c = P.CURVES[curve]
+    cd = CurveCodec(get_curve(curve))
+    cs = P.synthetic_circuit(c, 13, seed=9, num_inputs=2)
+    tw = toxic(c, 11)
+    cx = P.ctx(c)
+    opk = P.generate_parameters(cs, *tw)
+    want = P.generate_parameters(cs, *tw, scalars_only=True)
+    m = matrices_from_r1cs(cs)
+    pk, ex = oracle_setup(curve, m, tw, cx.g1_gen(), cx.g2_gen(), threads=3)
+    assert cd.fr.dec(ex["a"]) == want["a"] and cd.fr.dec(ex["b"]) == want["b"]
+    assert cd.fr.dec(ex["l"]) == want["l"] and cd.fr.dec(ex["h"]) == want["h"] and cd.fr.dec(ex["gamma_abc"]) == want["gamma_abc"]
+    ref = pk_to_abi(opk)
+    for name in ("a_query", "b_g1_query", "b_g2_query", "h_query", "l_query", "beta_g1", "delta_g1"):
+        assert np.array_equal(np.asarray(getattr(pk, name)).reshape(-1), np.asarray(getattr(ref, name)).reshape(-1)), name
+    for name in ("alpha_g1", "beta_g2", "gamma_g2", "delta_g2", "gamma_abc_g1"):
+        assert np.array_equal(np.asarray(getattr(pk.vk, name)).reshape(-1), np.asarray(getattr(ref.vk, name)).reshape(-1)), name
+
+
+@pytest.mark.parametrize("curve", ALL_CURVES)
+def test_oracle_window_parallel_msm_agrees(curve):
+    """ark-ec's window-parallel MSM schedule and the chunk-parallel default give the same group element."""
+    c = P.CURVES[curve]
+    cx = P.ctx(c)
+    cd = CurveCodec(get_curve(curve))
+    rng = P.Rng(61)
+    n = 300
+    sc = [rng.fr(c.r) for _ in range(n)]
+    g1 = cd.enc_g1([cx.g1_gen()])[0]
+    bases = orc.batch_mul_g1(c.cid, cd.nq, g1, cd.fr.enc([rng.fr(c.r) for _ in range(n)]), threads=2)
+    a = orc.msm_g1(c.cid, cd.nq, bases, cd.fr.bigint(sc), threads=3)
+    old = orc.set_msm_mode(1)
+    try:
+        b = orc.msm_g1(c.cid, cd.nq, bases, cd.fr.bigint(sc), threads=3)
+    finally:
+        orc.set_msm_mode(old)
+    assert np.array_equal(a, b)

@@ -59,3 +59,18 @@ def check_prepare_inputs(g, curve_name: str):
         g.prepare_inputs(vk, xs[:-1])
     with pytest.raises(MalformedKey):
         g.prepare_inputs(VerifyingKey(None, None, None, None, None), xs)
+
+
+def oracle_setup(curve_name: str, m, toxic_ints, g1=None, g2=None, threads=4):
+    """CPU trusted setup by the C++ oracle (orc.generate_parameters) -> (ProvingKey in ABI form, exponent dict)."""
+    import orc
+    from groth16_b200.params import GENERATORS
+    cp = get_curve(curve_name)
+    cd = CurveCodec(cp)
+    G = GENERATORS[cp.name]
+    g1a = cd.enc_g1([g1 or G["g1"]])[0]
+    g2a = cd.enc_g2([g2 or G["g2"]])[0]
+    k = orc.generate_parameters(cp.cid, cd.nq, m, cd.fr.enc(list(toxic_ints)), g1a, g2a, threads)
+    vk = VerifyingKey(k["alpha_g1"], k["beta_g2"], k["gamma_g2"], k["delta_g2"], k["gamma_abc_g1"])
+    pk = ProvingKey(vk, k["beta_g1"], k["delta_g1"], k["a_query"], k["b_g1_query"], k["b_g2_query"], k["h_query"], k["l_query"])
+    return pk, k["exponents"]

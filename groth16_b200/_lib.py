@@ -65,6 +65,12 @@ SIGNATURES = [
     ("g16_prove_partial_wait", C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     ("g16_witness_map", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
     ("g16_get_timings", C.c_int, [C.c_void_p, C.POINTER(Timings)]),
+    ("g16_comm_unique_id", C.c_int, [C.c_void_p]),
+    ("g16_comm_init", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]),
+    ("g16_prove_sharded", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    ("g16_prove_sharded_submit", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
+    ("g16_prove_sharded_wait", C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    ("g16_synthetic_r1cs", C.c_int, [C.c_int, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("g16_get_config", C.c_int, [C.c_void_p, C.POINTER(Config)]),
     ("g16_set_option", C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
 ]

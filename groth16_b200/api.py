@@ -349,6 +349,26 @@ class Groth16:
     def prove_partial_raw(self, r_limbs: np.ndarray, z_ptr, flags: int, out: np.ndarray):
         _check(self._lib.g16_prove_partial(self._ctx, _ptr(r_limbs), C.c_void_p(z_ptr), flags, _ptr(out)))
 
+    # ---- sharded proving with the NCCL exchange inside the library ----
+    def comm_unique_id(self) -> np.ndarray:
+        out = np.zeros(128, dtype=np.uint8)
+        _check(self._lib.g16_comm_unique_id(out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def comm_init(self, unique_id: np.ndarray, rank: int, world: int):
+        uid = np.ascontiguousarray(unique_id, dtype=np.uint8)
+        assert uid.size == 128
+        _check(self._lib.g16_comm_init(self._ctx, uid.ctypes.data_as(C.c_void_p), rank, world))
+
+    def prove_sharded_raw(self, r_limbs, s_limbs, z_ptr, flags: int, out: np.ndarray):
+        _check(self._lib.g16_prove_sharded(self._ctx, _ptr(r_limbs), _ptr(s_limbs), C.c_void_p(z_ptr), flags, _ptr(out)))
+
+    def prove_sharded_submit_raw(self, slot: int, r_limbs, s_limbs, z_ptr, flags: int):
+        _check(self._lib.g16_prove_sharded_submit(self._ctx, slot, _ptr(r_limbs), _ptr(s_limbs), C.c_void_p(z_ptr), flags))
+
+    def prove_sharded_wait_raw(self, slot: int, out: np.ndarray):
+        _check(self._lib.g16_prove_sharded_wait(self._ctx, slot, _ptr(out)))
+
     def prove_assemble_prepare(self, r, s):
         """start the (r, s)-only scalar multiplications on a helper thread (overlaps GPU work and the gather)"""
         self._asm_keep = (self._fr_arg(r), self._fr_arg(s))

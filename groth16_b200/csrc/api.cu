@@ -1,4 +1,5 @@
 // api.cu -- extern "C" surface of libg16b200.so (include/g16b200.h): argument checks, curve dispatch, error string.
+#include <dlfcn.h>
 #include <string>
 #include "engine.cuh"
 
@@ -6,6 +7,38 @@ namespace g16 {
 std::string& last_error_ref() {
   static thread_local std::string e;
   return e;
+}
+int fail(int code, const std::string& msg);   // out-of-line copy for translation units that do not include engine.cuh
+NcclApi& nccl_api() {
+  static NcclApi api;
+  return api;
+}
+bool NcclApi::load() {
+  if (handle) return true;
+  // 1. a libnccl the host process has already loaded (torch ships its own), 2. G16_NCCL_LIB, 3. the system library
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  for (const char* n : names)
+    if ((h = dlopen(n, RTLD_NOW | RTLD_NOLOAD))) break;
+  if (!h)
+    if (const char* e = getenv("G16_NCCL_LIB")) h = dlopen(e, RTLD_NOW | RTLD_GLOBAL);
+  if (!h)
+    for (const char* n : names)
+      if ((h = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+  if (!h) { err = std::string("dlopen(libnccl.so.2): ") + (dlerror() ? dlerror() : "not found"); return false; }
+  auto sym = [&](const char* n) { return dlsym(h, n); };
+  GetUniqueId = reinterpret_cast<int (*)(NcclUniqueId*)>(sym("ncclGetUniqueId"));
+  CommInitRank = reinterpret_cast<int (*)(void**, int, NcclUniqueId, int)>(sym("ncclCommInitRank"));
+  AllGather = reinterpret_cast<int (*)(const void*, void*, size_t, int, void*, cudaStream_t)>(sym("ncclAllGather"));
+  CommDestroy = reinterpret_cast<int (*)(void*)>(sym("ncclCommDestroy"));
+  GetErrorString = reinterpret_cast<const char* (*)(int)>(sym("ncclGetErrorString"));
+  if (!GetUniqueId || !CommInitRank || !AllGather || !CommDestroy || !GetErrorString) { err = "libnccl lacks an expected symbol"; return false; }
+  handle = h;
+  return true;
+}
+int fail(int code, const std::string& msg) {
+  last_error_ref() = msg;
+  return code;
 }
 IEngine* make_engine_bls381(int device, int* rc);
 IEngine* make_engine_bn254(int device, int* rc);
@@ -131,6 +164,34 @@ int g16_get_timings(const g16_ctx* ctx, g16_timings* out) {
   return G16_OK;
 }
 
+int g16_comm_unique_id(uint8_t* out128) {
+  if (!out128) return fail(G16_ERR_BAD_ARGUMENT, "null buffer");
+  NcclApi& api = nccl_api();
+  if (!api.load()) return fail(G16_ERR_CUDA, "NCCL is not available: " + api.err);
+  NcclUniqueId id;
+  const int rc = api.GetUniqueId(&id);
+  if (rc != 0) return fail(G16_ERR_CUDA, std::string("ncclGetUniqueId: ") + api.GetErrorString(rc));
+  memcpy(out128, id.internal, 128);
+  return G16_OK;
+}
+int g16_comm_init(g16_ctx* ctx, const uint8_t* id128, uint32_t rank, uint32_t world) {
+  CTX_OR_FAIL(ctx);
+  return ctx->eng->comm_init(id128, rank, world);
+}
+int g16_prove_sharded_submit(g16_ctx* ctx, int slot, const uint64_t* r, const uint64_t* s, const uint64_t* full_assignment, uint32_t flags) {
+  CTX_OR_FAIL(ctx);
+  return ctx->eng->sharded_submit(slot, r, s, full_assignment, flags);
+}
+int g16_prove_sharded_wait(g16_ctx* ctx, int slot, uint64_t* proof_out) {
+  CTX_OR_FAIL(ctx);
+  return ctx->eng->sharded_wait(slot, proof_out);
+}
+int g16_prove_sharded(g16_ctx* ctx, const uint64_t* r, const uint64_t* s, const uint64_t* full_assignment, uint32_t flags, uint64_t* proof_out) {
+  CTX_OR_FAIL(ctx);
+  const int rc = ctx->eng->sharded_submit(0, r, s, full_assignment, flags);
+  if (rc) return rc;
+  return ctx->eng->sharded_wait(0, proof_out);
+}
 int g16_get_config(const g16_ctx* ctx, g16_config* out) {
   CTX_OR_FAIL(ctx);
   return ctx->eng->get_config(out);

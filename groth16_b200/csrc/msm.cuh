@@ -38,10 +38,13 @@ struct MsmGeom {
   uint64_t max_entries;  // n * W
   int k0;            // sorted entries per thread in the level-0 accumulation (64 for large MSMs, less to fill the GPU)
   int ba;            // batched-affine pre-reduction rounds before the accumulation (msm_ba.cuh); 0 = none
+  int ba_pad;        // buckets are padded to multiples of 2^ba_pad sorted slots (>= ba; larger when the sorted list is
+                     // shared with an MSM that runs more rounds)
   int ba_m;          // batched-affine: additions per thread and round
   int ba_G;          // batched-affine: thread products per field inversion
   int ba_gcd;        // batched-affine: 1 = safegcd inversion, 0 = Fermat
   int acc_block;     // threads per block of the level-0 accumulation (32 / 64 / 128)
+  int ba_occ;        // batched-affine kernels: resident blocks per SM the register allocation targets (0 = default: 3 / 2)
 };
 
 static constexpr int MSM_K0_MAX = 64;
@@ -74,10 +77,12 @@ inline MsmGeom msm_geom(uint64_t n, int scalar_bits, int c_override = 0, int ne_
   g.max_entries = (uint64_t)n * g.W;
   g.k0 = MSM_K0_MAX;
   g.ba = 0;
-  g.ba_m = 16;
-  g.ba_G = 64;
+  g.ba_pad = 0;
+  g.ba_m = 32;
+  g.ba_G = 16;
   g.ba_gcd = 1;
   g.acc_block = 128;
+  g.ba_occ = 0;
   return g;
 }
 
@@ -570,15 +575,16 @@ static constexpr int MSM_TAIL_S = 2048;  // partial-list length at which the rem
 // that finishes the last list.
 static constexpr int MSM_BA_MAX_ROUNDS = 6;
 struct MsmBaPlan {
-  int R = 0;
+  int R = 0, pad = 0;
   uint64_t len[MSM_BA_MAX_ROUNDS + 1] = {0};   // len[r] = slots of list r (len[0]: padded sorted slots), upper bounds
   uint32_t m[MSM_BA_MAX_ROUNDS] = {0};
   uint64_t threads_max = 0;
   int k0_final = 0;
   void make(const MsmGeom& g) {
     R = g.ba < 0 ? 0 : (g.ba > MSM_BA_MAX_ROUNDS ? MSM_BA_MAX_ROUNDS : g.ba);
-    // every bucket is padded to a multiple of 2^R slots: at most 2^R - 1 extra slots per bucket
-    len[0] = R > 0 ? ((g.max_entries + (uint64_t)g.nkeys * ((1u << R) - 1)) >> R) << R : g.max_entries;
+    pad = g.ba_pad > R ? (g.ba_pad > MSM_BA_MAX_ROUNDS ? MSM_BA_MAX_ROUNDS : g.ba_pad) : R;
+    // every bucket is padded to a multiple of 2^pad slots: at most 2^pad - 1 extra slots per bucket
+    len[0] = pad > 0 ? ((g.max_entries + (uint64_t)g.nkeys * ((1u << pad) - 1)) >> pad) << pad : g.max_entries;
     threads_max = 0;
     for (int r = 0; r < R; r++) {
       len[r + 1] = len[r] >> 1;
@@ -676,10 +682,19 @@ struct MsmCounters {  // launch bookkeeping for bench.py's gpu_launches
 
 // Enqueue one MSM on `st`.  d_bases holds g.copies * g.n affine points (copy-major); d_scalars / d_skip are device
 // pointers, pair i uses the scalar at d_scalars + 8 * i * scalar_stride (stride = world size for a sharded key); the leaf arrays of the bucket reduction land in ws.h_leaf once the stream is synchronised (msm_finish).
+// The sorted (bucket-major, padded) entry list of an MSM, as another MSM over the SAME scalars, skip mask and geometry may
+// borrow it: B in G1 and B in G2 (prover.rs:101,113) share scalars, and their queries share the identity pattern
+// (b_g1_query[i] and b_g2_query[i] are both b_i(tau) times a generator), so one counting sort serves both.
+struct MsmSorted {
+  const uint32_t* sidx = nullptr;
+  const uint32_t* skey = nullptr;
+  const uint32_t* total0 = nullptr;
+  cudaEvent_t ready = nullptr;   // recorded on the lender's stream once the list is complete
+};
 template <class F, class FrF>
 cudaError_t msm_enqueue(cudaStream_t st, MsmWorkspace<F>& ws, const MsmGeom& g, const Affine<F>* d_bases,
                         const uint8_t* d_skip, const uint32_t* d_scalars, uint32_t scalar_stride, bool scalars_mont,
-                        MsmCounters* ctr, cudaEvent_t ev_acc0, cudaEvent_t ev_acc1) {
+                        MsmCounters* ctr, cudaEvent_t ev_acc0, cudaEvent_t ev_acc1, MsmSorted* lend, const MsmSorted* borrow) {
   cudaError_t e;
   if (g.n == 0) return cudaSuccess;
   if ((e = ws.prepare(g)) != cudaSuccess) return e;
@@ -691,27 +706,43 @@ cudaError_t msm_enqueue(cudaStream_t st, MsmWorkspace<F>& ws, const MsmGeom& g, 
   uint32_t* pending = ws.pending.template as<uint32_t>();
   XYZZ<F>* buckets = ws.buckets.template as<XYZZ<F>>();
   unsigned long long nl = 0;
-  cudaMemsetAsync(counters, 0, (size_t)(g.nkeys + 1) * 4, st);
   cudaMemsetAsync(pending, 0, 64 * 4, st);
   cudaMemsetAsync(buckets, 0, (size_t)g.nkeys * sizeof(XYZZ<F>), st);
-  const uint32_t nb = (g.n + 255) / 256;
-  msm_digits<FrF, false><<<nb, 256, 0, st>>>(d_scalars, scalar_stride, scalars_mont ? 1 : 0, d_skip, g, counters, nullptr, nullptr);
   const MsmBaPlan& bp = ws.bap;
-  const uint32_t pad_mask = bp.R > 0 ? (1u << bp.R) - 1 : 0;
-  const uint32_t sb = (g.nkeys + SCAN_BLOCK - 1) / SCAN_BLOCK;
-  msm_scan_blocks<<<sb, 1024, 0, st>>>(counters, g.nkeys, offsets, blocktot, pad_mask);
-  msm_scan_tops<<<1, 1024, 0, st>>>(blocktot, sb, offsets + g.nkeys);
-  msm_scan_fix<<<sb, 1024, 0, st>>>(offsets, g.nkeys, blocktot, counters);
-  msm_digits<FrF, true><<<nb, 256, 0, st>>>(d_scalars, scalar_stride, scalars_mont ? 1 : 0, d_skip, g, counters, sidx, skey);
-  nl += 5;
+  const uint32_t* total0 = offsets + g.nkeys;
+  if (borrow) {
+    // same scalars, mask and geometry as the lender: wait for its list instead of sorting again
+    cudaStreamWaitEvent(st, borrow->ready, 0);
+    sidx = const_cast<uint32_t*>(borrow->sidx);
+    skey = const_cast<uint32_t*>(borrow->skey);
+    total0 = borrow->total0;
+  } else {
+    cudaMemsetAsync(counters, 0, (size_t)(g.nkeys + 1) * 4, st);
+    const uint32_t nb = (g.n + 255) / 256;
+    msm_digits<FrF, false><<<nb, 256, 0, st>>>(d_scalars, scalar_stride, scalars_mont ? 1 : 0, d_skip, g, counters, nullptr, nullptr);
+    const uint32_t pad_mask = bp.pad > 0 ? (1u << bp.pad) - 1 : 0;
+    const uint32_t sb = (g.nkeys + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    msm_scan_blocks<<<sb, 1024, 0, st>>>(counters, g.nkeys, offsets, blocktot, pad_mask);
+    msm_scan_tops<<<1, 1024, 0, st>>>(blocktot, sb, offsets + g.nkeys);
+    msm_scan_fix<<<sb, 1024, 0, st>>>(offsets, g.nkeys, blocktot, counters);
+    msm_digits<FrF, true><<<nb, 256, 0, st>>>(d_scalars, scalar_stride, scalars_mont ? 1 : 0, d_skip, g, counters, sidx, skey);
+    nl += 5;
+    if (pad_mask) {
+      msm_pad_fill<<<(g.nkeys + 255) / 256, 256, 0, st>>>(counters, offsets, g.nkeys, sidx, skey);
+      nl += 1;
+    }
+    if (lend) {
+      lend->sidx = sidx;
+      lend->skey = skey;
+      lend->total0 = total0;
+      if (lend->ready) cudaEventRecord(lend->ready, st);
+    }
+  }
   // batched-affine rounds: the (padded) sorted slots shrink 2^R-fold to a list of partial bucket sums (msm_ba.cuh)
   const Affine<F>* acc_bases = d_bases;
   const uint32_t* acc_sidx = sidx;
-  const uint32_t* total0 = offsets + g.nkeys;
   if (ev_acc0) cudaEventRecord(ev_acc0, st);
   if (bp.R > 0) {
-    msm_pad_fill<<<(g.nkeys + 255) / 256, 256, 0, st>>>(counters, offsets, g.nkeys, sidx, skey);
-    nl += 1;
     Affine<F>* lists[2] = {ws.ba_l0.template as<Affine<F>>(), ws.ba_l1.template as<Affine<F>>()};
     for (int r = 0; r < bp.R; r++) {
       BaRound<F> a;
@@ -727,9 +758,18 @@ cudaError_t msm_enqueue(cudaStream_t st, MsmWorkspace<F>& ws, const MsmGeom& g, 
       a.pre2 = ws.ba_pre2.template as<F>();
       a.out = lists[r & 1];
       const uint64_t T = ba_threads(bp.len[r + 1], a.m), lanes = (T + a.G - 1) / a.G;
-      ba_forward_kernel<F><<<(unsigned)((T + 127) / 128), 128, 0, st>>>(a);
+      const unsigned nblk = (unsigned)((T + 127) / 128);
+      bool occ3 = false;
+      if constexpr (sizeof(F) > 48) occ3 = g.ba_occ == 3;   // the 3-blocks-per-SM build exists for Fq2 points only
+      if constexpr (sizeof(F) > 48) {
+        if (occ3) ba_forward_kernel<F, 3><<<nblk, 128, 0, st>>>(a);
+      }
+      if (!occ3) ba_forward_kernel<F><<<nblk, 128, 0, st>>>(a);
       ba_combine_kernel<F><<<(unsigned)((lanes + 31) / 32), 32, 0, st>>>(a);
-      ba_backward_kernel<F><<<(unsigned)((T + 127) / 128), 128, 0, st>>>(a);
+      if constexpr (sizeof(F) > 48) {
+        if (occ3) ba_backward_kernel<F, 3><<<nblk, 128, 0, st>>>(a);
+      }
+      if (!occ3) ba_backward_kernel<F><<<nblk, 128, 0, st>>>(a);
       nl += 3;
     }
     acc_bases = lists[(bp.R - 1) & 1];
@@ -928,7 +968,8 @@ cudaError_t fb_batch_mul(cudaStream_t st, const Affine<F>& gen, const FrF* d_sca
 // declares them `extern template` (keeps ptxas work parallel across make jobs).
 #define G16_MSM_TEMPLATES(X, F, FrF)                                                                                     \
   X cudaError_t msm_enqueue<F, FrF>(cudaStream_t, MsmWorkspace<F>&, const MsmGeom&, const Affine<F>*, const uint8_t*,    \
-                                    const uint32_t*, uint32_t, bool, MsmCounters*, cudaEvent_t, cudaEvent_t);            \
+                                    const uint32_t*, uint32_t, bool, MsmCounters*, cudaEvent_t, cudaEvent_t, MsmSorted*, \
+                                    const MsmSorted*);                                                                   \
   X cudaError_t msm_prepare_query<F>(cudaStream_t, Affine<F>*, uint32_t, int, int, uint8_t*);                            \
   X cudaError_t fb_batch_mul<F, FrF>(cudaStream_t, const Affine<F>&, const FrF*, uint64_t, Affine<F>*, XYZZ<F>*);
 

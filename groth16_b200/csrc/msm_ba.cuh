@@ -217,18 +217,22 @@ G16_HD void ba_backward(const BaRound<F>& a, uint64_t t) {
 }
 
 #ifdef __CUDACC__
-template <class F>
-struct BaCfg { static constexpr int MIN_BLOCKS = sizeof(F) <= 48 ? 3 : 2; };
-template <class F>
-__global__ void __launch_bounds__(128, BaCfg<F>::MIN_BLOCKS) ba_forward_kernel(BaRound<F> a) {
+// Resident blocks per SM the register allocation aims at.  Single-field points: 3 (the bodies need ~125 registers, so 4 fit
+// anyway).  Fq2 points: 2 = the whole backward body in 254 registers without spilling (8 warps per SM); the OCC3 variant
+// caps the allocation at 168 registers for 12 warps per SM and lets ptxas spill the coldest operands to local memory,
+// which at this footprint (3 x 128 threads x a few hundred bytes) stays L1-resident.  Selected per MSM (MsmGeom::ba_occ).
+template <class F, int OCC>
+struct BaCfg { static constexpr int MIN_BLOCKS = OCC > 0 ? OCC : (sizeof(F) <= 48 ? 3 : 2); };
+template <class F, int OCC = 0>
+__global__ void __launch_bounds__(128, BaCfg<F, OCC>::MIN_BLOCKS) ba_forward_kernel(BaRound<F> a) {
   ba_forward<F>(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
 }
 template <class F>
 __global__ void __launch_bounds__(32) ba_combine_kernel(BaRound<F> a) {
   ba_combine<F>(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
 }
-template <class F>
-__global__ void __launch_bounds__(128, BaCfg<F>::MIN_BLOCKS) ba_backward_kernel(BaRound<F> a) {
+template <class F, int OCC = 0>
+__global__ void __launch_bounds__(128, BaCfg<F, OCC>::MIN_BLOCKS) ba_backward_kernel(BaRound<F> a) {
   ba_backward<F>(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
 }
 #endif  // __CUDACC__

@@ -38,70 +38,34 @@ def _fr(gen, r):
 
 
 def synthetic_r1cs(curve, log_n: int, seed: int = 0, num_inputs: int = 1):
+    """The synthetic R1CS of SURVEY.md section 8d through g16_synthetic_r1cs (csrc/workload.cu: host code of the library, no
+    GPU needed; a Python loop over 2^24 constraints would take minutes).  One public input."""
+    import ctypes as C
+    from . import _lib
+    if num_inputs != 1:
+        raise ValueError("the generator has exactly one public input")
     c = get_curve(curve)
     cd = CurveCodec(c)
-    r = c.r
-    ninst = 1 + num_inputs
+    ninst = 2
     nc = (1 << log_n) - ninst
-    if nc < num_inputs + 1:
+    if log_n < 3:
         raise ValueError("domain too small")
-    gen = _splitmix(seed)
-    rs = np.random.RandomState(seed & 0x7FFFFFFF)
-    nwit = 2 + nc - num_inputs
-    # variable creation order: two seeds, then one product per constraint
-    cols = np.empty(2 + nc, dtype=np.uint32)
-    cols[0], cols[1] = ninst, ninst + 1
-    vals = [0] * (2 + nc)
-    vals[0], vals[1] = _fr(gen, r), _fr(gen, r)
-    # p, q uniform over the variables that exist when constraint i is written
-    u1 = rs.random_sample(nc)
-    u2 = rs.random_sample(nc)
-    avail = np.arange(2, 2 + nc, dtype=np.float64)
-    ps = np.minimum((u1 * avail).astype(np.int64), (avail - 1).astype(np.int64))
-    qs = np.minimum((u2 * avail).astype(np.int64), (avail - 1).astype(np.int64))
-    ks_lo = rs.randint(0, 1 << 62, size=nc, dtype=np.int64)
-    ks_hi = rs.randint(0, 1 << 62, size=nc, dtype=np.int64)
-    ks = [0] * nc
-    n_w = 2
-    n_i = 0
-    first_input = nc - num_inputs
-    for i in range(nc):
-        k = (int(ks_hi[i]) << 62) | int(ks_lo[i])   # 124-bit coefficient; its size is irrelevant to the prover
-        ks[i] = k
-        v = (vals[ps[i]] + k) * vals[qs[i]] % r
-        vals[2 + i] = v
-        if i >= first_input:
-            cols[2 + i] = 1 + n_i
-            n_i += 1
-        else:
-            cols[2 + i] = ninst + n_w
-            n_w += 1
-    assert n_w == nwit and n_i == num_inputs
-    # CSR: A = [(1, col_p), (k, One)], B = [(1, col_q)], C = [(1, col_new)]
-    one = cd.fr.enc1(1)
-    a_rp = np.arange(0, 2 * nc + 1, 2, dtype=np.uint32)
+    nwit = nc + 1
     a_col = np.empty(2 * nc, dtype=np.uint32)
-    a_col[0::2] = cols[ps]
-    a_col[1::2] = 0
     a_val = np.empty((2 * nc, 4), dtype=np.uint64)
-    a_val[0::2] = one
-    a_val[1::2] = cd.fr.enc(ks)
+    b_col = np.empty(nc, dtype=np.uint32)
+    c_col = np.empty(nc, dtype=np.uint32)
+    z = np.zeros((ninst + nwit, 4), dtype=np.uint64)
+    vp = lambda x: x.ctypes.data_as(C.c_void_p)
+    rc = _lib.load().g16_synthetic_r1cs(c.cid, log_n, seed & 0xFFFFFFFFFFFFFFFF, vp(a_col), vp(a_val), vp(b_col), vp(c_col), vp(z))
+    if rc != 0:
+        raise ValueError(_lib.last_error())
+    one = np.ascontiguousarray(cd.fr.enc1(1))
+    a_rp = np.arange(0, 2 * nc + 1, 2, dtype=np.uint32)
     b_rp = np.arange(0, nc + 1, dtype=np.uint32)
-    b_col = cols[qs].astype(np.uint32)
-    b_val = np.tile(one, (nc, 1))
-    c_rp = np.arange(0, nc + 1, dtype=np.uint32)
-    c_col = cols[2:].astype(np.uint32)
-    c_val = np.tile(one, (nc, 1))
-    m = ConstraintMatrices(ninst, nwit, nc, (a_rp, a_col, np.ascontiguousarray(a_val)),
-                           (b_rp, np.ascontiguousarray(b_col), np.ascontiguousarray(b_val)),
-                           (c_rp, np.ascontiguousarray(c_col), np.ascontiguousarray(c_val)))
-    # full assignment: One, inputs, witnesses (in column order)
-    full = [0] * (ninst + nwit)
-    full[0] = 1
-    for j in range(2 + nc):
-        full[cols[j]] = vals[j]
-    z = np.ascontiguousarray(cd.fr.enc(full))
-    return m, z, full[1:ninst]
+    ones = np.ascontiguousarray(np.broadcast_to(one, (nc, 4)))
+    m = ConstraintMatrices(ninst, nwit, nc, (a_rp, a_col, a_val), (b_rp, b_col, ones), (b_rp.copy(), c_col, ones.copy()))
+    return m, z, cd.fr.dec(z[1:ninst])
 
 
 def dummy_r1cs(curve, num_variables: int, num_constraints: int, seed: int = 0):

@@ -152,6 +152,22 @@ int g16_prove_partial_wait(g16_ctx* ctx, int slot, uint64_t* partial_out);
 /* limbs per partial record: 4*2*N64 + 4*N64 */
 int g16_partial_limbs(const g16_ctx* ctx);
 
+/* Sharded proving with the exchange INSIDE the library: one NCCL all-gather (over NVLink / NVSwitch) of three partial points
+ * per rank, issued by the library on its own stream (no reference counterpart -- ark-groth16 is a
+ * single-process CPU prover).  One process per GPU:
+ *   rank 0: g16_comm_unique_id(id)  ->  the launcher broadcasts the 128 bytes (torch.distributed / MPI / a file)
+ *   every rank: g16_comm_init(ctx, id, rank, world); g16_pk_load(ctx, pk, rank, world);
+ *   per proof, every rank with the same (r, s, assignment): g16_prove_sharded(...) -> every rank gets the same proof.
+ * libnccl is resolved at run time (the copy the host process already loaded, else $G16_NCCL_LIB, else libnccl.so.2).
+ * The submit / wait pair is the pipelined form (two slots, as g16_prove_submit / g16_prove_wait). */
+int g16_comm_unique_id(uint8_t* out128);
+int g16_comm_init(g16_ctx* ctx, const uint8_t* id128, uint32_t rank, uint32_t world);
+int g16_prove_sharded(g16_ctx* ctx, const uint64_t* r, const uint64_t* s, const uint64_t* full_assignment, uint32_t flags,
+                      uint64_t* proof_out);
+int g16_prove_sharded_submit(g16_ctx* ctx, int slot, const uint64_t* r, const uint64_t* s, const uint64_t* full_assignment,
+                             uint32_t flags);
+int g16_prove_sharded_wait(g16_ctx* ctx, int slot, uint64_t* proof_out);
+
 /* ---- witness map alone on the resident circuit (R1CSToQAP::witness_map_from_matrices, r1cs_to_qap.rs:172-235):
  * h_out receives domain_size Montgomery Fr coefficients. */
 int g16_witness_map(g16_ctx* ctx, const uint64_t* full_assignment, uint32_t flags, uint64_t* h_out);
@@ -184,11 +200,20 @@ typedef struct {
   int32_t reserved[4];
 } g16_config;
 int g16_get_config(const g16_ctx* ctx, g16_config* out);
-/* key: "msm_ba", "msm_ba_g2", "ba_m", "ba_g", "ba_inv_gcd", "acc_k0_g1", "acc_k0_g2", "acc_block" (the G16_* environment
+/* key: "msm_ba", "msm_ba_g2", "ba_m", "ba_g", "ba_inv_gcd", "acc_k0_g1", "acc_k0_g2", "acc_block", "share_b_sort", "ba_occ_g2", and -- effective at the next
+ * g16_pk_load / g16_setup -- "msm_ne", "msm_c", "msm_maxcopies" (the G16_* environment
  * variables of INTEGRATION.md section 6, read once at g16_ctx_create, in lower case without the prefix).  Takes effect
  * from the next proof; results never depend on these knobs. */
 int g16_set_option(g16_ctx* ctx, const char* key, int64_t value);
 uint32_t g16_domain_log(const g16_ctx* ctx); /* log2 of the resident circuit's domain size */
+
+/* ---- benchmark / test helper (no reference counterpart: arkworks users bring their own circuits) -----------------
+ * The non-degenerate synthetic R1CS of SURVEY.md section 8d, generated on the host: constraint i is
+ * (z_p + k_i) * z_q = z_new; nc = 2^log_n - 2 constraints, 2 instance variables (One, one public input),
+ * nc + 1 witness variables.  Caller-allocated outputs: a_col[2 nc], a_val[2 nc] Montgomery Fr (row i = (1, col_p), (k_i, One)),
+ * b_col[nc], c_col[nc] (coefficients 1), full_assignment[nc + 3] Montgomery Fr.  Needs no GPU and no context. */
+int g16_synthetic_r1cs(int curve, uint32_t log_n, uint64_t seed, uint32_t* a_col, uint64_t* a_val, uint32_t* b_col,
+                       uint32_t* c_col, uint64_t* full_assignment);
 
 #ifdef __cplusplus
 }

@@ -122,8 +122,14 @@ extern "C" {
     pub fn g16_prove_wait(ctx: *mut g16_ctx, slot: c_int, proof_out: *mut u64) -> c_int;
     pub fn g16_prove_partial_submit(ctx: *mut g16_ctx, slot: c_int, r: *const u64, full_assignment: *const u64, flags: u32) -> c_int;
     pub fn g16_prove_partial_wait(ctx: *mut g16_ctx, slot: c_int, partial_out: *mut u64) -> c_int;
+    pub fn g16_comm_unique_id(out128: *mut u8) -> c_int;
+    pub fn g16_comm_init(ctx: *mut g16_ctx, id128: *const u8, rank: u32, world: u32) -> c_int;
+    pub fn g16_prove_sharded(ctx: *mut g16_ctx, r: *const u64, s: *const u64, full_assignment: *const u64, flags: u32, proof_out: *mut u64) -> c_int;
+    pub fn g16_prove_sharded_submit(ctx: *mut g16_ctx, slot: c_int, r: *const u64, s: *const u64, full_assignment: *const u64, flags: u32) -> c_int;
+    pub fn g16_prove_sharded_wait(ctx: *mut g16_ctx, slot: c_int, proof_out: *mut u64) -> c_int;
     pub fn g16_witness_map(ctx: *mut g16_ctx, full_assignment: *const u64, flags: u32, h_out: *mut u64) -> c_int;
     pub fn g16_get_timings(ctx: *const g16_ctx, out: *mut g16_timings) -> c_int;
+    pub fn g16_synthetic_r1cs(curve: c_int, log_n: u32, seed: u64, a_col: *mut u32, a_val: *mut u64, b_col: *mut u32, c_col: *mut u32, full_assignment: *mut u64) -> c_int;
     pub fn g16_get_config(ctx: *const g16_ctx, out: *mut g16_config) -> c_int;
     pub fn g16_set_option(ctx: *mut g16_ctx, key: *const c_char, value: i64) -> c_int;
 }

@@ -71,6 +71,24 @@ def test_ntt_three_pass_plan(curve, log_n):
             assert np.array_equal(got, want), (curve, log_n, inverse, coset)
 
 
+@pytest.mark.parametrize("curve,log_n", [("bn254", 14), ("bls12_381", 15), ("bls12_377", 16), ("bn254", 17), ("bls12_381", 19),
+                                         ("bn254", 21), ("bls12_381", 22)])
+def test_ntt_tma_plans(curve, log_n):
+    """Every shape of the TMA-tiled plan (csrc/ntt_tma.cuh): one strided pass with 2^4 .. 2^10 rows (log n = 14 .. 20), two
+    strided passes (21, 22), forward + coset-inverse; and the generic passes (g16_set_option ntt_tma 0) give the same bits."""
+    g = engine(curve)
+    cid = P.CURVES[curve].cid
+    vals = rand_fr_mont(np.random.RandomState(2000 + log_n), 1 << log_n)
+    for inverse, coset in ((False, False), (True, True)):
+        want = orc.ntt(cid, log_n, vals, inverse=inverse, coset=coset, threads=THREADS)
+        assert np.array_equal(g.ntt_log(log_n, vals, inverse=inverse, coset=coset), want), (curve, log_n, inverse, coset, "tma")
+        g.set_option("ntt_tma", 0)
+        try:
+            assert np.array_equal(g.ntt_log(log_n, vals, inverse=inverse, coset=coset), want), (curve, log_n, inverse, coset, "generic")
+        finally:
+            g.set_option("ntt_tma", 1)
+
+
 def _setup(curve, m):
     g = engine(curve)
     G = GENERATORS[curve]

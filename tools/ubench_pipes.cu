@@ -10,6 +10,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cuda_runtime.h>
+#include "../groth16_b200/csrc/fp.cuh"
 
 constexpr int ITER = 4096, CH = 8;
 
@@ -36,6 +37,47 @@ __global__ void __launch_bounds__(256) k(uint64_t* out, uint32_t seed, double ds
 #pragma unroll
   for (int i = 0; i < CH; i++) s += a[i] + c[i] + (uint64_t)d[i];
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// The library's 384-bit Montgomery product in isolation: CHAINS independent dependent-product chains per thread, resident
+// warps per SM set by the dynamic shared memory request.  Upper bound of what any kernel built on fp.cuh can reach.
+template <int CHAINS>
+__global__ void __launch_bounds__(128) mulchain(uint32_t* out, int iters) {
+  using F = g16::Fp<g16::BLS381_FqP>;
+  F x[CHAINS], y = F::r2();
+  for (int c = 0; c < CHAINS; c++) { x[c] = F::one(); x[c].v[0] += threadIdx.x + c; }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int c = 0; c < CHAINS; c++) x[c] = F::mul(x[c], y);
+  }
+  uint32_t s = 0;
+  for (int c = 0; c < CHAINS; c++) s += x[c].v[3];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+template <int CHAINS>
+static void run_mul(int warps_per_sm, int sms, double mhz) {
+  const int blocks_per_sm = warps_per_sm / 4;
+  const int smem = (227 * 1024) / blocks_per_sm - 1024;   // forces exactly blocks_per_sm resident blocks
+  cudaFuncSetAttribute(mulchain<CHAINS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const int blocks = sms * blocks_per_sm, iters = 2000;
+  uint32_t* out;
+  cudaMalloc(&out, (size_t)blocks * 128 * 4);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  mulchain<CHAINS><<<blocks, 128, smem>>>(out, iters);
+  cudaDeviceSynchronize();
+  cudaEventRecord(e0);
+  mulchain<CHAINS><<<blocks, 128, smem>>>(out, iters);
+  cudaEventRecord(e1);
+  cudaEventSynchronize(e1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  const double muls = (double)blocks * 128 * iters * CHAINS / (ms * 1e-3);
+  printf("{\"test\": \"fq_mul_bls381\", \"chains_per_thread\": %d, \"warps_per_sm\": %d, \"ms\": %.4f, \"muls_per_s\": %.4e, \"imad_wide_per_s\": %.4e, "
+         "\"imad_wide_lanes_per_clk_per_sm\": %.2f, \"err\": \"%s\"}\n",
+         CHAINS, warps_per_sm, ms, muls, muls * 288, muls * 288 / (mhz * 1e6) / sms, cudaGetErrorString(cudaGetLastError()));
+  cudaFree(out);
 }
 
 template <int MODE>
@@ -75,5 +117,7 @@ int main() {
   run<4>("mix_imadwide_dfma", 2, p.multiProcessorCount, mhz);
   run<5>("mix_imadwide_iadd", 2, p.multiProcessorCount, mhz);
   run<6>("mix_dfma_iadd", 2, p.multiProcessorCount, mhz);
+  for (int w : {4, 8, 12, 16, 24, 32, 48}) run_mul<1>(w, p.multiProcessorCount, mhz);
+  for (int w : {4, 8, 12, 16, 24}) run_mul<2>(w, p.multiProcessorCount, mhz);
   return 0;
 }

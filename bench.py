@@ -56,6 +56,8 @@ def parse():
                          "points) and is what `value` reports; 'replicas' lets every GPU prove its own proofs (weak scaling, no "
                          "communication: BASELINE config 5) and reports that as `value`; 'auto' (default) = 'shard' for `value` "
                          "and additionally measures the replicas, reported under the secondary key \"replicas\"")
+    ap.add_argument("--check-oracle", action="store_true",
+                    help="N > 1: rank 0 also proves once with the CPU oracle and compares bit for bit (N = 1 always does, as its cpu_baseline)")
     ap.add_argument("--record", default="", help="also append the JSON line to this file (profiles/r02_bench_*.json)")
     return ap.parse_args()
 
@@ -294,8 +296,28 @@ def run_cuda(a):
     nq = g.nq
     G = GENERATORS[g.curve.name]
     want_shard = world > 1 and a.mode != "replicas"
+    # ---- residency plan: precomputed multiples of every base as far as HBM allows ----
+    nvars = m.num_instance_variables + m.num_witness_variables
+    key_bytes = nvars * 8 * nq * (4 * 2 + 4)              # a, b_g1, h, l (G1) + b_g2, packed affine, one copy
+    mem_total = torch.cuda.get_device_properties(dev).total_memory
+    share = world if want_shard else 1
+    ne = 1
+    while ne < 16 and key_bytes * ((16 + ne - 1) // ne) / share > 0.5 * mem_total:
+        ne *= 2
+    big = key_bytes * 16 > 0.5 * mem_total                # the unsharded key with all copies does not fit one GPU
+    if os.environ.get("G16_BENCH_FORCE_BIG"):              # exercise the large-key path (mint without copies, re-load) at any size
+        big = True
+    residency = {"key_bytes_one_copy": int(key_bytes), "msm_ne": ne, "copies": (16 + ne - 1) // ne,
+                 "resident_key_bytes_per_gpu": int(key_bytes * ((16 + ne - 1) // ne) / share)}
     t = time.time()
-    pk = g.generate_parameters_with_qap(m, *TOXIC, G["g1"], G["g2"], export=(want_shard or not a.no_cpu_baseline))
+    if big:
+        g.set_option("msm_ne", 0)                         # mint the key without precomputed multiples, re-load it with the plan
+        g.set_option("proof_slots", 1)
+    pk = g.generate_parameters_with_qap(m, *TOXIC, G["g1"], G["g2"], export=(want_shard or big or not a.no_cpu_baseline))
+    if big:
+        g.set_option("msm_ne", ne)
+        if not want_shard:
+            g.load_proving_key(pk, 0, 1)
     t_setup = time.time() - t
     r = np.ascontiguousarray(cd.fr.enc1(123456789))
     s = np.ascontiguousarray(cd.fr.enc1(987654321))
@@ -404,13 +426,13 @@ def run_cuda(a):
     sampler = ClockSampler(local) if rank == 0 else None
     secondary = None
     if want_shard:
-        arm = Arm("shard", a.inflight or 2)
+        arm = Arm("shard", a.inflight or (1 if big else 2))
         main = arm.measure(1, sampler)
         par = (f"msm-shard{world}: one proof per step, pair i of every MSM on rank i mod {world}, witness map replicated, "
                "3 partial points per rank (768 B) all-gathered by ONE ncclAllGather issued inside the library "
                "(g16_prove_sharded), every rank finishes the same proof")
         scaling = "strong"
-        if a.mode == "auto":
+        if a.mode == "auto" and not big:
             g.load_proving_key(pk, 0, 1)          # full key resident again: every rank proves on its own
             rep = Arm("single", a.inflight or 1).measure(world)
             assert np.array_equal(rep["proof"], main["proof"]), "sharded and single-GPU proofs differ"
@@ -481,6 +503,14 @@ def run_cuda(a):
                 cpu = {"value": 1.0 / csec, "unit": "proofs/s", "cores": threads, "kind": "port",
                        "sample": f"1 full proof of the same workload ({csec:.2f} s wall: witness map {tms[0]:.0f} ms, MSMs+assembly "
                                  f"{tms[1]:.0f} ms), restated ark CPU path; proof bit-identical to the CUDA proof"}
+        oracle_check = None
+        if world > 1 and a.check_oracle:
+            threads = host_threads(a.cpu_threads)
+            cproof, csec, tms = cpu_prove_once(a, cd, nq, pk, m, z_np, r, s, threads)
+            if not np.array_equal(cproof, first):
+                raise SystemExit("PARITY FAILURE: sharded CUDA proof != CPU oracle proof")
+            oracle_check = {"proof_bit_identical_to_cpu_oracle": True, "cpu_seconds": csec, "cores": threads,
+                            "witness_map_ms": tms[0], "msm_ms": tms[1]}
         line = {
             "metric": metric_name(a), "value": main["value"], "unit": "proofs/s", "n_gpus": world, "steps": a.steps,
             "warmup": max(a.warmup, 3), "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": scaling,
@@ -498,6 +528,8 @@ def run_cuda(a):
             "latency_ms_single_proof": main["latency_ms_single_proof"],
             "e2e": main["e2e"],
             "gpu_launches": main["launches"],
+            "proof_sha256": __import__("hashlib").sha256(first.tobytes()).hexdigest(),
+            "residency": residency,
             "clocks": main["clocks"],
             "setup_s": {"workload": t_work, "gpu_setup_and_key_residency": t_setup},
         }
@@ -506,6 +538,8 @@ def run_cuda(a):
             line["config"]["env"] = knobs
         if secondary:
             line["replicas"] = secondary
+        if oracle_check:
+            line["oracle_check"] = oracle_check
         if roof:
             line["roofline"] = roof
             line["kernels"] = kern

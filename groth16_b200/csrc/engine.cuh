@@ -183,7 +183,7 @@ struct Engine : IEngine {
   struct Slot {
     cudaStream_t st_main = nullptr, st_msm[5] = {};
     cudaEvent_t ev_start = nullptr, ev_z = nullptr, ev_h = nullptr, ev_m0[5] = {}, ev_m1[5] = {}, ev_a0[5] = {}, ev_a1[5] = {};
-    cudaEvent_t ev_bsort = nullptr;   // B-in-G1's sorted entry list is complete (B-in-G2 borrows it)
+    cudaEvent_t ev_bsort = nullptr;   // B-in-G2's sorted entry list is complete (B-in-G1 borrows it)
     MsmSorted b_sorted;
     DevBuf d_z, d_a, d_b, d_c, d_t, d_h;
     MsmWorkspace<Fq> ws1[4];
@@ -257,6 +257,7 @@ struct Engine : IEngine {
   }
   // entries per level-0 thread, from the number of resident accumulation threads of this device
   int sm_count = 148;
+  int proof_slots = NSLOTS;   // slots the caller will use (g16_set_option "proof_slots" 1 halves the workspace the key must leave room for)
   bool ba_allowed = true;   // cleared by pk_load / setup when the rounds' work lists would not fit in device memory
   MsmGeom with_k0(MsmGeom g, bool g2) const {
     g.k0 = msm_pick_k0(g.max_entries, (uint64_t)sm_count * 128 * (g2 ? 2 : 3), g2 ? 16 : 8);
@@ -314,7 +315,7 @@ struct Engine : IEngine {
     }
     size_t fr = 0, tot = 0;
     if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) return;
-    if (2 * need + (4ull << 30) > fr) {
+    if ((uint64_t)proof_slots * need + (4ull << 30) > fr) {
       ba_allowed = false;
       refresh_geoms();
     }
@@ -331,7 +332,8 @@ struct Engine : IEngine {
     else if (k == "acc_k0_g2") tune.k0_g2 = (int)v;
     else if (k == "acc_block") tune.acc_block = (int)v;
     else if (k == "ba_occ_g2") tune.ba_occ_g2 = v == 3 ? 3 : 0;
-    else if (k == "ntt_tma") { use_ntt_tma = v != 0; return G16_OK; }
+    else if (k == "ntt_tma") { use_ntt_tma = v < 0 ? -1 : (v != 0 ? 1 : 0); return G16_OK; }
+    else if (k == "proof_slots") { proof_slots = v <= 1 ? 1 : NSLOTS; if (have_pk) decide_ba_memory(); return G16_OK; }
     // residency knobs: take effect at the NEXT g16_pk_load / g16_setup (they decide how many precomputed multiples a key keeps)
     else if (k == "msm_ne") { cfg_ne = (int)std::max(0ll, std::min(v, 32ll)); return G16_OK; }
     else if (k == "msm_c") { cfg_c = (v < 0 || v > 24) ? 0 : (int)v; return G16_OK; }
@@ -515,10 +517,14 @@ struct Engine : IEngine {
 
   // One transform: the TMA-tiled passes (ntt_tma.cuh) from 2^14 points up, the generic passes (ntt.cuh) below that or
   // when the tensor-map encoder is unavailable / switched off (g16_set_option "ntt_tma" 0).
-  bool use_ntt_tma = true;
+  // Measured on a B200 (profiles/r02_sweep_c.jsonl): at 2^20 the 128 KB tiles are only 256 CTAs for 148 SMs (1.7 waves, one
+  // CTA per SM) and the witness map takes 2.61 ms against 2.03 ms with the generic passes; the TMA plan is therefore the
+  // default only from 2^22 points (>= 1024 tiles).  1 = always (from 2^14), 0 = never, -1 = automatic.
+  int use_ntt_tma = -1;
   void ntt_any(cudaStream_t st, const NttDomain<Fr>& d, bool inverse, const Fr* src, Fr* work, Fr* dst, int load_mode, const Fr* ltab,
                const Fr* in_b, const Fr* in_c, const Fr& load_cst, int store_mode, const Fr* stab, const Fr& store_cst) {
-    if (use_ntt_tma && ntt2_run<Fr>(st, d, inverse, src, work, dst, load_mode, ltab, in_b, in_c, load_cst, store_mode, stab, store_cst, &ntt_launches))
+    const bool tma = use_ntt_tma > 0 || (use_ntt_tma < 0 && d.L >= 22);
+    if (tma && ntt2_run<Fr>(st, d, inverse, src, work, dst, load_mode, ltab, in_b, in_c, load_cst, store_mode, stab, store_cst, &ntt_launches))
       return;
     ntt_run<Fr>(st, d, inverse, src, work, dst, load_mode, ltab, in_b, in_c, load_cst, store_mode, stab, store_cst, &ntt_launches);
   }
@@ -555,10 +561,10 @@ struct Engine : IEngine {
     Fr* A = sl.d_a.template as<Fr>(); Fr* B = sl.d_b.template as<Fr>(); Fr* C = sl.d_c.template as<Fr>(); Fr* T = sl.d_t.template as<Fr>(); Fr* H = sl.d_h.template as<Fr>();
     const Fr zero = Fr::zero();
     for (Fr* X : {A, B, C}) {
-      // domain.ifft_in_place (r1cs_to_qap.rs:201-202,220)
-      ntt_any(st, dom, true, X, X, T, NTT_LOAD_PLAIN, nullptr, nullptr, nullptr, zero, NTT_STORE_MUL_CONST, nullptr, dom.n_inv);
-      // coset_domain.fft_in_place (r1cs_to_qap.rs:204-207,221)
-      ntt_any(st, dom, false, T, T, X, NTT_LOAD_MUL_TABLE, dom.coset_fwd, nullptr, nullptr, zero, NTT_STORE_PLAIN, nullptr, zero);
+      // domain.ifft_in_place (r1cs_to_qap.rs:201-202,220) followed by coset_domain.fft_in_place (:204-207,221): the inverse
+      // transform's n^-1 and the coset pre-scaling g^i are one multiplication by the table n^-1 g^i at the second load
+      ntt_any(st, dom, true, X, X, T, NTT_LOAD_PLAIN, nullptr, nullptr, nullptr, zero, NTT_STORE_PLAIN, nullptr, zero);
+      ntt_any(st, dom, false, T, T, X, NTT_LOAD_MUL_TABLE, dom.coset_fwd_ninv, nullptr, nullptr, zero, NTT_STORE_PLAIN, nullptr, zero);
     }
     // (a*b - c) * Z^-1 fused into the load of coset_domain.ifft_in_place (r1cs_to_qap.rs:209,223-232)
     ntt_any(st, dom, true, A, T, H, NTT_LOAD_AB_MINUS_C, nullptr, B, C, dom.z_inv, NTT_STORE_MUL_TABLE, dom.coset_inv, zero);
@@ -932,7 +938,8 @@ struct Engine : IEngine {
       sl.run[m] = cnt > 0 && !(m == M_B1 && r_zero);                     // prover.rs:98: B in G1 skipped when r == 0
       sl.tm.msm_pairs[m] = sl.run[m] ? cnt : 0;
     }
-    const int order[5] = {M_L, M_A, M_B1, M_B2, M_H};                    // H last: it waits for the witness map
+    const int order[5] = {M_L, M_A, M_B2, M_B1, M_H};                    // H last: it waits for the witness map; B2 (higher
+                                                                         // stream priority) sorts, B1 borrows its sorted list
     for (int oi = 0; oi < 5; oi++) {
       const int m = order[oi];
       NvtxSpan span_msm(span_of(m));
@@ -942,11 +949,12 @@ struct Engine : IEngine {
       if (sl.run[m]) {
         const uint32_t* sc = src[m] + q[m].lo * 8;   // first owned scalar; the digit kernel strides by `world`
         cudaError_t e;
-        // B in G1 and B in G2 run over the same scalars and identity pattern: B2 borrows B1's sorted entry list
+        // B in G1 and B in G2 run over the same scalars and identity pattern: one counting sort serves both.  B2 sorts
+        // (its stream has the higher priority and its tail is the longest), B1 borrows the list.
         const bool share = share_b_sort && sl.run[M_B1] && sl.run[M_B2];
-        if (m == M_B1 && share) { sl.b_sorted = MsmSorted{}; sl.b_sorted.ready = sl.ev_bsort; }
-        if (m == M_B2) e = msm_enqueue<Fq2, Fr>(st, sl.ws2, sl.geom[m], q[m].bases.template as<A2>(), q[m].mask.template as<uint8_t>(), sc, world, true, &ctr, sl.ev_a0[m], sl.ev_a1[m], nullptr, share ? &sl.b_sorted : nullptr);
-        else e = msm_enqueue<Fq, Fr>(st, sl.ws1[m], sl.geom[m], q[m].bases.template as<A1>(), q[m].mask.template as<uint8_t>(), sc, world, true, &ctr, sl.ev_a0[m], sl.ev_a1[m], (m == M_B1 && share) ? &sl.b_sorted : nullptr, nullptr);
+        if (m == M_B2 && share) { sl.b_sorted = MsmSorted{}; sl.b_sorted.ready = sl.ev_bsort; }
+        if (m == M_B2) e = msm_enqueue<Fq2, Fr>(st, sl.ws2, sl.geom[m], q[m].bases.template as<A2>(), q[m].mask.template as<uint8_t>(), sc, world, true, &ctr, sl.ev_a0[m], sl.ev_a1[m], share ? &sl.b_sorted : nullptr, nullptr);
+        else e = msm_enqueue<Fq, Fr>(st, sl.ws1[m], sl.geom[m], q[m].bases.template as<A1>(), q[m].mask.template as<uint8_t>(), sc, world, true, &ctr, sl.ev_a0[m], sl.ev_a1[m], nullptr, (m == M_B1 && share) ? &sl.b_sorted : nullptr);
         if (e != cudaSuccess) return fail(G16_ERR_CUDA, std::string("msm_enqueue: ") + cudaGetErrorString(e));
       }
       G16_CUDA(cudaEventRecord(sl.ev_m1[m], st));

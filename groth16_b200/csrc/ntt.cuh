@@ -106,7 +106,8 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(NttPass<Fr> a) {
 #pragma unroll
       for (int q = 0; q < 8; q++) { x0.v[q] = sm[q][e0]; x1.v[q] = sm[q][e1]; }
       const Fr u = Fr::add(x0, x1);
-      const Fr v = Fr::mul(Fr::sub(x0, x1), w);
+      Fr v = Fr::sub(x0, x1);
+      if (s != a.L - 1) v = Fr::mul(v, w);   // the last stage of a transform only has the twiddle omega^0 = 1
 #pragma unroll
       for (int q = 0; q < 8; q++) { sm[q][e0] = u.v[q]; sm[q][e1] = v.v[q]; }
     }
@@ -185,6 +186,7 @@ struct NttDomain {
   Fr* tw_inv = nullptr;     // omega^-i     i < n/2
   Fr* coset_fwd = nullptr;  // g^i          i < n
   Fr* coset_inv = nullptr;  // n^-1 g^-i    i < n
+  Fr* coset_fwd_ninv = nullptr;  // n^-1 g^i  i < n: iFFT's n^-1 and the following coset pre-scaling in one multiplication
   Fr n_inv, z_inv;          // n^-1 ; (g^n - 1)^-1   (Montgomery form, host copies)
   Fr omega;
   void release() {
@@ -192,7 +194,8 @@ struct NttDomain {
     if (tw_inv) cudaFree(tw_inv);
     if (coset_fwd) cudaFree(coset_fwd);
     if (coset_inv) cudaFree(coset_inv);
-    tw_fwd = tw_inv = coset_fwd = coset_inv = nullptr;
+    if (coset_fwd_ninv) cudaFree(coset_fwd_ninv);
+    tw_fwd = tw_inv = coset_fwd = coset_inv = coset_fwd_ninv = nullptr;
     L = -1;
   }
 };
@@ -231,6 +234,7 @@ cudaError_t ntt_domain_build(NttDomain<Fr>& d, int L, cudaStream_t st, unsigned 
   if ((e = cudaMalloc(&d.tw_inv, half * sizeof(Fr))) != cudaSuccess) return e;
   if ((e = cudaMalloc(&d.coset_fwd, d.n * sizeof(Fr))) != cudaSuccess) return e;
   if ((e = cudaMalloc(&d.coset_inv, d.n * sizeof(Fr))) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&d.coset_fwd_ninv, d.n * sizeof(Fr))) != cudaSuccess) return e;
   const Fr omega = fr_domain_root<Fr>(L);
   const Fr omega_inv = Fr::inv(omega);
   const Fr g = fr_generator<Fr>();
@@ -250,6 +254,7 @@ cudaError_t ntt_domain_build(NttDomain<Fr>& d, int L, cudaStream_t st, unsigned 
   launch(d.tw_inv, half, omega_inv, Fr::one());
   launch(d.coset_fwd, d.n, g, Fr::one());
   launch(d.coset_inv, d.n, g_inv, d.n_inv);
+  launch(d.coset_fwd_ninv, d.n, g, d.n_inv);
   d.L = L;
   return cudaGetLastError();
 }

@@ -351,13 +351,13 @@ class Groth16:
 
     # ---- sharded proving with the NCCL exchange inside the library ----
     def comm_unique_id(self) -> np.ndarray:
-        out = np.zeros(128, dtype=np.uint8)
+        out = np.zeros(256, dtype=np.uint8)
         _check(self._lib.g16_comm_unique_id(out.ctypes.data_as(C.c_void_p)))
         return out
 
     def comm_init(self, unique_id: np.ndarray, rank: int, world: int):
         uid = np.ascontiguousarray(unique_id, dtype=np.uint8)
-        assert uid.size == 128
+        assert uid.size == 256
         _check(self._lib.g16_comm_init(self._ctx, uid.ctypes.data_as(C.c_void_p), rank, world))
 
     def prove_sharded_raw(self, r_limbs, s_limbs, z_ptr, flags: int, out: np.ndarray):

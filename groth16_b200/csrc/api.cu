@@ -31,8 +31,13 @@ bool NcclApi::load() {
   CommInitRank = reinterpret_cast<int (*)(void**, int, NcclUniqueId, int)>(sym("ncclCommInitRank"));
   AllGather = reinterpret_cast<int (*)(const void*, void*, size_t, int, void*, cudaStream_t)>(sym("ncclAllGather"));
   CommDestroy = reinterpret_cast<int (*)(void*)>(sym("ncclCommDestroy"));
+  Send = reinterpret_cast<int (*)(const void*, size_t, int, int, void*, cudaStream_t)>(sym("ncclSend"));
+  Recv = reinterpret_cast<int (*)(void*, size_t, int, int, void*, cudaStream_t)>(sym("ncclRecv"));
+  Broadcast = reinterpret_cast<int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)>(sym("ncclBroadcast"));
+  GroupStart = reinterpret_cast<int (*)()>(sym("ncclGroupStart"));
+  GroupEnd = reinterpret_cast<int (*)()>(sym("ncclGroupEnd"));
   GetErrorString = reinterpret_cast<const char* (*)(int)>(sym("ncclGetErrorString"));
-  if (!GetUniqueId || !CommInitRank || !AllGather || !CommDestroy || !GetErrorString) { err = "libnccl lacks an expected symbol"; return false; }
+  if (!GetUniqueId || !CommInitRank || !AllGather || !CommDestroy || !GetErrorString || !Send || !Recv || !Broadcast || !GroupStart || !GroupEnd) { err = "libnccl lacks an expected symbol"; return false; }
   handle = h;
   return true;
 }
@@ -168,10 +173,12 @@ int g16_comm_unique_id(uint8_t* out128) {
   if (!out128) return fail(G16_ERR_BAD_ARGUMENT, "null buffer");
   NcclApi& api = nccl_api();
   if (!api.load()) return fail(G16_ERR_CUDA, "NCCL is not available: " + api.err);
-  NcclUniqueId id;
-  const int rc = api.GetUniqueId(&id);
-  if (rc != 0) return fail(G16_ERR_CUDA, std::string("ncclGetUniqueId: ") + api.GetErrorString(rc));
-  memcpy(out128, id.internal, 128);
+  for (int k = 0; k < 2; k++) {   // one id per communicator: point all-gather, witness-map exchange
+    NcclUniqueId id;
+    const int rc = api.GetUniqueId(&id);
+    if (rc != 0) return fail(G16_ERR_CUDA, std::string("ncclGetUniqueId: ") + api.GetErrorString(rc));
+    memcpy(out128 + 128 * k, id.internal, 128);
+  }
   return G16_OK;
 }
 int g16_comm_init(g16_ctx* ctx, const uint8_t* id128, uint32_t rank, uint32_t world) {

@@ -109,6 +109,11 @@ struct NcclApi {
   int (*GetUniqueId)(NcclUniqueId*) = nullptr;
   int (*CommInitRank)(void**, int, NcclUniqueId, int) = nullptr;
   int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   std::string err;
@@ -191,6 +196,7 @@ struct Engine : IEngine {
     g16_timings tm{};
     // state of the submission in flight
     bool busy = false, serial = false, have_s = false;
+    bool split_wm = false;   // this submission spreads the witness map over the ranks (sharded proof with a communicator)
     bool run[5] = {};
     MsmGeom geom[5] = {};
     Fr r, s;
@@ -259,7 +265,8 @@ struct Engine : IEngine {
   int sm_count = 148;
   int proof_slots = NSLOTS;   // slots the caller will use (g16_set_option "proof_slots" 1 halves the workspace the key must leave room for)
   bool ba_allowed = true;   // cleared by pk_load / setup when the rounds' work lists would not fit in device memory
-  MsmGeom with_k0(MsmGeom g, bool g2) const {
+  uint32_t ba_allowed_mask = 0x1f;   // per MSM (bit m): the work lists of MSM m fit next to the key and the other MSMs' lists
+  MsmGeom with_k0(MsmGeom g, bool g2, int m = -1) const {
     g.k0 = msm_pick_k0(g.max_entries, (uint64_t)sm_count * 128 * (g2 ? 2 : 3), g2 ? 16 : 8);
     // G2 additions are ~3x longer: 32 entries per thread (twice the thread count) shortens the last partial wave (-13 %)
     if (g2 && g.k0 > 32) g.k0 = 32;
@@ -267,7 +274,8 @@ struct Engine : IEngine {
     if (k >= 4 && k <= 1024) g.k0 = k;
     // batched-affine pre-reduction (msm_ba.cuh) for MSMs with at least 2^18 entries
     const int r = g2 ? tune.ba_g2 : tune.ba_g1;
-    g.ba = (ba_allowed && r > 0 && g.max_entries >= (1u << 18)) ? std::min(r, (int)MSM_BA_MAX_ROUNDS) : 0;
+    const bool allowed = ba_allowed && (m < 0 || ((ba_allowed_mask >> m) & 1));
+    g.ba = (allowed && r > 0 && g.max_entries >= (1u << 18)) ? std::min(r, (int)MSM_BA_MAX_ROUNDS) : 0;
     g.ba_m = tune.ba_m;
     g.ba_G = tune.ba_G;
     g.ba_gcd = tune.ba_gcd;
@@ -279,7 +287,7 @@ struct Engine : IEngine {
   bool share_b_sort_wanted = true;
   void refresh_geoms() {   // after a knob changed: same shards, new launch geometry
     for (int m = 0; m < 5; m++)
-      if (q[m].hi > q[m].lo) q[m].geom = with_k0(q[m].geom, m == M_B2);
+      if (q[m].hi > q[m].lo) q[m].geom = with_k0(q[m].geom, m == M_B2, m);
     // one padding for the list B1 lends to B2
     const int pad = std::max(q[M_B1].geom.ba, q[M_B2].geom.ba);
     q[M_B1].geom.ba_pad = share_b_sort ? pad : q[M_B1].geom.ba;
@@ -304,21 +312,24 @@ struct Engine : IEngine {
   // key when two slots' worth would not fit next to the resident key (e.g. 2^24 constraints on one GPU).
   void decide_ba_memory() {
     ba_allowed = true;
+    ba_allowed_mask = 0x1f;
     refresh_geoms();
-    uint64_t need = 0;
-    for (int m = 0; m < 5; m++) {
-      if (q[m].hi <= q[m].lo) continue;
-      MsmBaPlan bp;
-      bp.make(q[m].geom);
-      need += (m == M_B2) ? bp.template extra_bytes<Fq2>() : bp.template extra_bytes<Fq>();
-      need += bp.len[0] * 8;
-    }
     size_t fr = 0, tot = 0;
     if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) return;
-    if ((uint64_t)proof_slots * need + (4ull << 30) > fr) {
-      ba_allowed = false;
-      refresh_geoms();
+    // greedy, G1 MSMs first (their lists are half the size of the G2 ones): keep the rounds for an MSM while the lists of all
+    // MSMs granted so far fit `proof_slots` times into the free memory, with 10 GB to spare for everything else
+    const uint64_t margin = 10ull << 30;
+    uint64_t used = 0;
+    uint32_t mask = 0;
+    for (int m : {M_H, M_L, M_A, M_B1, M_B2}) {
+      if (q[m].hi <= q[m].lo) { mask |= 1u << m; continue; }
+      MsmBaPlan bp;
+      bp.make(q[m].geom);
+      const uint64_t need = ((m == M_B2) ? bp.template extra_bytes<Fq2>() : bp.template extra_bytes<Fq>()) + bp.len[0] * 8;
+      if ((uint64_t)proof_slots * (used + need) + margin <= fr) { used += need; mask |= 1u << m; }
     }
+    ba_allowed_mask = mask;
+    refresh_geoms();
   }
   int set_option(const char* key, long long v) override {
     if (any_busy()) return fail(G16_ERR_BAD_ARGUMENT, "a proof is in flight");
@@ -333,6 +344,7 @@ struct Engine : IEngine {
     else if (k == "acc_block") tune.acc_block = (int)v;
     else if (k == "ba_occ_g2") tune.ba_occ_g2 = v == 3 ? 3 : 0;
     else if (k == "ntt_tma") { use_ntt_tma = v < 0 ? -1 : (v != 0 ? 1 : 0); return G16_OK; }
+    else if (k == "wm_split") { split_wm_wanted = v != 0; return G16_OK; }
     else if (k == "proof_slots") { proof_slots = v <= 1 ? 1 : NSLOTS; if (have_pk) decide_ba_memory(); return G16_OK; }
     // residency knobs: take effect at the NEXT g16_pk_load / g16_setup (they decide how many precomputed multiples a key keeps)
     else if (k == "msm_ne") { cfg_ne = (int)std::max(0ll, std::min(v, 32ll)); return G16_OK; }
@@ -517,13 +529,15 @@ struct Engine : IEngine {
 
   // One transform: the TMA-tiled passes (ntt_tma.cuh) from 2^14 points up, the generic passes (ntt.cuh) below that or
   // when the tensor-map encoder is unavailable / switched off (g16_set_option "ntt_tma" 0).
-  // Measured on a B200 (profiles/r02_sweep_c.jsonl): at 2^20 the 128 KB tiles are only 256 CTAs for 148 SMs (1.7 waves, one
-  // CTA per SM) and the witness map takes 2.61 ms against 2.03 ms with the generic passes; the TMA plan is therefore the
-  // default only from 2^22 points (>= 1024 tiles).  1 = always (from 2^14), 0 = never, -1 = automatic.
-  int use_ntt_tma = -1;
+  // Measured on a B200 (profiles/r02_sweep_c.jsonl, r02_bench_bls12_377_22_synthetic.json): the TMA plan halves the
+  // passes' DRAM traffic but loses on time -- at 2^20 its 128 KB tiles are only 256 CTAs for 148 SMs (1.7 waves, one CTA
+  // per SM, no overlap of load / butterflies / store): witness map 2.61 ms against 2.03 ms with the generic passes, and
+  // 9.9 ms against 8.1 ms at 2^22.  It is therefore OFF by default and selectable (g16_set_option "ntt_tma" 1) --
+  // DESIGN.md section 3 has the analysis.  1 = from 2^14 points, 0 / -1 = generic passes.
+  int use_ntt_tma = 0;
   void ntt_any(cudaStream_t st, const NttDomain<Fr>& d, bool inverse, const Fr* src, Fr* work, Fr* dst, int load_mode, const Fr* ltab,
                const Fr* in_b, const Fr* in_c, const Fr& load_cst, int store_mode, const Fr* stab, const Fr& store_cst) {
-    const bool tma = use_ntt_tma > 0 || (use_ntt_tma < 0 && d.L >= 22);
+    const bool tma = use_ntt_tma > 0;
     if (tma && ntt2_run<Fr>(st, d, inverse, src, work, dst, load_mode, ltab, in_b, in_c, load_cst, store_mode, stab, store_cst, &ntt_launches))
       return;
     ntt_run<Fr>(st, d, inverse, src, work, dst, load_mode, ltab, in_b, in_c, load_cst, store_mode, stab, store_cst, &ntt_launches);
@@ -568,6 +582,41 @@ struct Engine : IEngine {
     }
     // (a*b - c) * Z^-1 fused into the load of coset_domain.ifft_in_place (r1cs_to_qap.rs:209,223-232)
     ntt_any(st, dom, true, A, T, H, NTT_LOAD_AB_MINUS_C, nullptr, B, C, dom.z_inv, NTT_STORE_MUL_TABLE, dom.coset_inv, zero);
+  }
+
+  // The witness map of a SHARDED proof (the chains a, b, c are independent, r1cs_to_qap.rs:201-207,
+  // 220-221): chain v (iFFT then coset FFT of one vector) runs on rank v mod world, the three results meet on rank
+  // 3 mod world (ncclSend / ncclRecv of 32 B * n each over NVLink), which forms (a*b - c)/Z and the last coset iFFT
+  // (r1cs_to_qap.rs:209,223-232), and h is broadcast to every rank for its share of the H MSM.  Per rank at most 3 of the 7
+  // transforms instead of 7; everything is enqueued on the slot's main stream, no host synchronisation.
+  int witness_map_split(Slot& sl) {
+    NcclApi& api = nccl_api();
+    cudaStream_t st = sl.st_main;
+    Fr* V[3] = {sl.d_a.template as<Fr>(), sl.d_b.template as<Fr>(), sl.d_c.template as<Fr>()};
+    Fr* T = sl.d_t.template as<Fr>();
+    Fr* H = sl.d_h.template as<Fr>();
+    const Fr zero = Fr::zero();
+    const int w = (int)comm_world, me = (int)comm_rank, fin = 3 % w;
+    const size_t bytes = (size_t)sizeof(Fr) << L;
+    for (int v = 0; v < 3; v++) {
+      if (v % w != me) continue;
+      ntt_any(st, dom, true, V[v], V[v], T, NTT_LOAD_PLAIN, nullptr, nullptr, nullptr, zero, NTT_STORE_PLAIN, nullptr, zero);
+      ntt_any(st, dom, false, T, T, V[v], NTT_LOAD_MUL_TABLE, dom.coset_fwd_ninv, nullptr, nullptr, zero, NTT_STORE_PLAIN, nullptr, zero);
+    }
+    int rc = api.GroupStart();
+    for (int v = 0; v < 3 && rc == 0; v++) {
+      const int src = v % w;
+      if (src == fin) continue;
+      if (me == src) rc = api.Send(V[v], bytes, /*ncclUint8*/ 1, fin, nccl_comm_wm, st);
+      if (me == fin && rc == 0) rc = api.Recv(V[v], bytes, 1, src, nccl_comm_wm, st);
+    }
+    if (rc == 0) rc = api.GroupEnd(); else api.GroupEnd();
+    if (rc != 0) return fail(G16_ERR_CUDA, std::string("witness-map exchange (ncclSend/Recv): ") + api.GetErrorString(rc));
+    if (me == fin)
+      ntt_any(st, dom, true, V[0], T, H, NTT_LOAD_AB_MINUS_C, nullptr, V[1], V[2], dom.z_inv, NTT_STORE_MUL_TABLE, dom.coset_inv, zero);
+    rc = api.Broadcast(H, H, bytes, 1, fin, nccl_comm_wm, st);
+    if (rc != 0) return fail(G16_ERR_CUDA, std::string("witness-map broadcast (ncclBroadcast): ") + api.GetErrorString(rc));
+    return G16_OK;
   }
 
   int witness_map_evals(uint32_t log_n, const uint64_t* a, const uint64_t* b, const uint64_t* c, uint64_t* h) override {
@@ -885,7 +934,11 @@ struct Engine : IEngine {
     r1cs_matvec<Fr>(sl.st_main, cs, sl.d_z.template as<Fr>(), num_constraints, num_inputs, n, sl.d_a.template as<Fr>(),
                     sl.d_b.template as<Fr>(), sl.d_c.template as<Fr>());
     ntt_launches++;
-    witness_map_device(sl, dom);
+    if (sl.split_wm && nccl_comm_wm) {
+      if ((rc = witness_map_split(sl))) return rc;
+    } else {
+      witness_map_device(sl, dom);
+    }
     G16_CUDA(cudaGetLastError());
     G16_CUDA(cudaEventRecord(sl.ev_h, sl.st_main));
     return G16_OK;
@@ -1152,7 +1205,9 @@ struct Engine : IEngine {
   // in XYZZ coordinates (no inversion on the exchange path): 2 * 4 * Fq + 4 * Fq2 limbs = 768 B on BLS12-381.  One
   // ncclAllGather of that record on a dedicated high-priority stream, then every rank adds the records in rank order and
   // finishes the same proof (EC addition is exactly associative and commutative: bit-identical for any world size).
-  void* nccl_comm = nullptr;
+  void* nccl_comm = nullptr;      // all-gather of the partial proof points (stream st_comm)
+  void* nccl_comm_wm = nullptr;   // witness-map exchange (send / recv / broadcast on the proof slot's main stream)
+  bool split_wm_wanted = true;    // g16_set_option "wm_split"
   uint32_t comm_rank = 0, comm_world = 0;
   cudaStream_t st_comm = nullptr;
   DevBuf d_comm_send, d_comm_recv;
@@ -1161,7 +1216,8 @@ struct Engine : IEngine {
   static constexpr size_t REC_LIMBS = 2 * 4 * (size_t)NQ64 + 4 * 2 * (size_t)NQ64;   // A_k, C_k (XYZZ G1), B2_k (XYZZ G2)
   void comm_release() {
     if (nccl_comm && nccl_api().CommDestroy) nccl_api().CommDestroy(nccl_comm);
-    nccl_comm = nullptr;
+    if (nccl_comm_wm && nccl_api().CommDestroy) nccl_api().CommDestroy(nccl_comm_wm);
+    nccl_comm = nccl_comm_wm = nullptr;
     if (h_comm_send) cudaFreeHost(h_comm_send);
     if (h_comm_recv) cudaFreeHost(h_comm_recv);
     h_comm_send = h_comm_recv = nullptr;
@@ -1170,7 +1226,7 @@ struct Engine : IEngine {
     if (st_comm) cudaStreamDestroy(st_comm);
     st_comm = nullptr;
   }
-  int comm_init(const uint8_t* id128, uint32_t rk, uint32_t wd) override {
+  int comm_init(const uint8_t* id128, uint32_t rk, uint32_t wd) override {   // id128: TWO NCCL unique ids (256 bytes)
     if (!id128 || wd == 0 || rk >= wd) return fail(G16_ERR_BAD_ARGUMENT, "bad unique id / rank / world");
     G16_NOT_BUSY();
     NcclApi& api = nccl_api();
@@ -1181,6 +1237,9 @@ struct Engine : IEngine {
     memcpy(id.internal, id128, 128);
     int rc = api.CommInitRank(&nccl_comm, (int)wd, id, (int)rk);
     if (rc != 0) { nccl_comm = nullptr; return fail(G16_ERR_CUDA, std::string("ncclCommInitRank: ") + api.GetErrorString(rc)); }
+    memcpy(id.internal, id128 + 128, 128);
+    rc = api.CommInitRank(&nccl_comm_wm, (int)wd, id, (int)rk);
+    if (rc != 0) { nccl_comm_wm = nullptr; return fail(G16_ERR_CUDA, std::string("ncclCommInitRank (witness map): ") + api.GetErrorString(rc)); }
     comm_rank = rk;
     comm_world = wd;
     int prio_lo = 0, prio_hi = 0;
@@ -1203,7 +1262,10 @@ struct Engine : IEngine {
     if (!s) return fail(G16_ERR_BAD_ARGUMENT, "null buffer");
     if (!nccl_comm) return fail(G16_ERR_BAD_ARGUMENT, "g16_comm_init must precede g16_prove_sharded");
     if (comm_world != world || comm_rank != rank) return fail(G16_ERR_BAD_ARGUMENT, "the key's (rank, world) differs from the communicator's");
-    return submit(slots[slot], r, s, z, flags);
+    slots[slot].split_wm = split_wm_wanted && comm_world > 1;
+    const int rc = submit(slots[slot], r, s, z, flags);
+    slots[slot].split_wm = false;
+    return rc;
   }
   template <class PT>
   static uint64_t* put_xyzz(uint64_t* p, const PT& x) { memcpy(p, &x, sizeof(PT)); return p + sizeof(PT) / 8; }

@@ -7,7 +7,7 @@ the proof is bit-identical for any world size; NCCL has no user-defined reductio
 Two exchanges exist:
   * in the library (default on GPUs, `ShardedProver(native=True)`): g16_comm_init + g16_prove_sharded -- the library issues
     ONE ncclAllGather of three XYZZ points per rank (A_k, B2_k, C_k = s A_k + r B1_k + L_k + H_k; 768 B on BLS12-381) on
-    its own high-priority stream and finishes the proof; torch.distributed only carries the 128-byte NCCL unique id once.
+    its own high-priority stream and finishes the proof; torch.distributed only carries the two NCCL unique ids (256 bytes) once.
   * host-plumbed (`native=False`; the gloo CPU tests, or a launcher without NCCL): g16_prove_partial -> all_gather of five
     affine points per rank through torch.distributed -> g16_prove_assemble.
 """
@@ -37,10 +37,10 @@ def all_gather_partials(partial: np.ndarray, device=None) -> np.ndarray:
 
 
 def broadcast_unique_id(groth16, rank: int, device=None) -> np.ndarray:
-    """rank 0 asks the library for an NCCL unique id (g16_comm_unique_id); torch.distributed broadcasts the 128 bytes"""
+    """rank 0 asks the library for an NCCL unique id (g16_comm_unique_id); torch.distributed broadcasts the 256 bytes"""
     import torch
     import torch.distributed as dist
-    uid = groth16.comm_unique_id() if rank == 0 else np.zeros(128, dtype=np.uint8)
+    uid = groth16.comm_unique_id() if rank == 0 else np.zeros(256, dtype=np.uint8)
     t = torch.from_numpy(uid.copy())
     if device is not None:
         t = t.to(device)

@@ -155,13 +155,17 @@ int g16_partial_limbs(const g16_ctx* ctx);
 /* Sharded proving with the exchange INSIDE the library: one NCCL all-gather (over NVLink / NVSwitch) of three partial points
  * per rank, issued by the library on its own stream (no reference counterpart -- ark-groth16 is a
  * single-process CPU prover).  One process per GPU:
- *   rank 0: g16_comm_unique_id(id)  ->  the launcher broadcasts the 128 bytes (torch.distributed / MPI / a file)
+ *   rank 0: g16_comm_unique_id(id)  ->  the launcher broadcasts the G16_COMM_ID_BYTES bytes (torch.distributed / MPI / a file)
  *   every rank: g16_comm_init(ctx, id, rank, world); g16_pk_load(ctx, pk, rank, world);
  *   per proof, every rank with the same (r, s, assignment): g16_prove_sharded(...) -> every rank gets the same proof.
  * libnccl is resolved at run time (the copy the host process already loaded, else $G16_NCCL_LIB, else libnccl.so.2).
- * The submit / wait pair is the pipelined form (two slots, as g16_prove_submit / g16_prove_wait). */
-int g16_comm_unique_id(uint8_t* out128);
-int g16_comm_init(g16_ctx* ctx, const uint8_t* id128, uint32_t rank, uint32_t world);
+ * The submit / wait pair is the pipelined form (two slots, as g16_prove_submit / g16_prove_wait).
+ * With a communicator the witness map is spread over the ranks as well (option "wm_split", default 1): the chains a, b, c
+ * (r1cs_to_qap.rs:201-207,220-221) run on ranks 0, 1, 2 (mod world), meet on rank 3 mod world over ncclSend / ncclRecv
+ * (32 B * n each), which runs (a*b - c)/Z and the last coset iFFT, and h is broadcast (ncclBroadcast) for the H MSM. */
+#define G16_COMM_ID_BYTES 256 /* two NCCL unique ids: one communicator for the point all-gather, one for the witness map */
+int g16_comm_unique_id(uint8_t* out /* G16_COMM_ID_BYTES */);
+int g16_comm_init(g16_ctx* ctx, const uint8_t* id /* G16_COMM_ID_BYTES */, uint32_t rank, uint32_t world);
 int g16_prove_sharded(g16_ctx* ctx, const uint64_t* r, const uint64_t* s, const uint64_t* full_assignment, uint32_t flags,
                       uint64_t* proof_out);
 int g16_prove_sharded_submit(g16_ctx* ctx, int slot, const uint64_t* r, const uint64_t* s, const uint64_t* full_assignment,

@@ -9,13 +9,14 @@
 set -u
 TAG=${1:-r02}; CURVE=${2:-bls12_381}; LOGN=${3:-20}; shift 3 2>/dev/null
 O=gpurun_out; mkdir -p $O
+export G16_PROFILE_TAG=$TAG
 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file $O/${TAG}_launches.csv \
     python tools/profile_run.py $CURVE $LOGN "$@" > $O/${TAG}_launches.log 2>&1
 ncu --set full --clock-control none --profile-from-start off -f -o $O/${TAG}_full \
     python tools/profile_run.py $CURVE $LOGN "$@" > $O/${TAG}_full.log 2>&1
 ncu -i $O/${TAG}_full.ncu-rep --page raw --csv > $O/${TAG}_full_raw.csv 2>> $O/${TAG}_full.log
 rm -f $O/${TAG}_full.ncu-rep
-for k in ba_backward_kernel msm_accum_l0 ntt_pass; do
+for k in ba_backward_kernel; do
   ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:$k -c 1 -f -o $O/${TAG}_$k \
       python tools/profile_run.py $CURVE $LOGN "$@" > $O/${TAG}_$k.log 2>&1
 done

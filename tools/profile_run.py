@@ -29,3 +29,10 @@ torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStop()
 print(g.timings())
 print(g.config())
+import json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bench import kernel_rev
+tag = os.environ.get("G16_PROFILE_TAG")
+if tag:
+    json.dump({"kernel_rev": kernel_rev(), "config": g.config(), "curve": curve, "log_n": log_n, "options": opts},
+              open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", f"{tag}_meta.json"), "w"))

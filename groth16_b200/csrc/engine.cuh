@@ -250,6 +250,11 @@ struct Engine : IEngine {
     int k0_g2 = 0;
     int acc_block = 128;
     int ba_occ_g2 = 0;    // 3: Fq2 batched-affine kernels compiled for 3 resident blocks per SM (168 registers, spills)
+    // The rounds cost ~0.12 ms of latency each (forward / combine / backward launches, one inversion per combine lane) and save
+    // ~0.10 ns per G1 entry, ~0.35 ns per G2 entry: below these entry counts (the per-rank shards of an 8-way proof have 2.1 M /
+    // 1.1 M) the plain XYZZ accumulation is faster (profiles/r02g_shard8.jsonl: 8.8 vs 10.9 ms per sharded step).
+    long long ba_min_g1 = 4ll << 20;
+    long long ba_min_g2 = 3ll << 20;
   } tune;
   MsmGeom pick_geom(uint64_t cnt) const {
     if (cfg_ne <= 0) return msm_geom(cnt, FR_BITS, cfg_c, 0);
@@ -275,7 +280,8 @@ struct Engine : IEngine {
     // batched-affine pre-reduction (msm_ba.cuh) for MSMs with at least 2^18 entries
     const int r = g2 ? tune.ba_g2 : tune.ba_g1;
     const bool allowed = ba_allowed && (m < 0 || ((ba_allowed_mask >> m) & 1));
-    g.ba = (allowed && r > 0 && g.max_entries >= (1u << 18)) ? std::min(r, (int)MSM_BA_MAX_ROUNDS) : 0;
+    const uint64_t min_entries = (uint64_t)std::max(1ll << 18, g2 ? tune.ba_min_g2 : tune.ba_min_g1);
+    g.ba = (allowed && r > 0 && g.max_entries >= min_entries) ? std::min(r, (int)MSM_BA_MAX_ROUNDS) : 0;
     g.ba_m = tune.ba_m;
     g.ba_G = tune.ba_G;
     g.ba_gcd = tune.ba_gcd;
@@ -343,6 +349,8 @@ struct Engine : IEngine {
     else if (k == "acc_k0_g2") tune.k0_g2 = (int)v;
     else if (k == "acc_block") tune.acc_block = (int)v;
     else if (k == "ba_occ_g2") tune.ba_occ_g2 = v == 3 ? 3 : 0;
+    else if (k == "ba_min_entries_g1") tune.ba_min_g1 = std::max(0ll, v);
+    else if (k == "ba_min_entries_g2") tune.ba_min_g2 = std::max(0ll, v);
     else if (k == "ntt_tma") { use_ntt_tma = v < 0 ? -1 : (v != 0 ? 1 : 0); return G16_OK; }
     else if (k == "wm_split") { split_wm_wanted = v != 0; return G16_OK; }
     else if (k == "proof_slots") { proof_slots = v <= 1 ? 1 : NSLOTS; if (have_pk) decide_ba_memory(); return G16_OK; }

@@ -307,11 +307,13 @@ def test_msm_skewed_scalars_large():
     _skewed_msm_check()
 
 
-def _set_ba(rounds_g1, rounds_g2, **kw):
+def _set_ba(rounds_g1, rounds_g2, min_entries=0, **kw):
     for name in ALL_CURVES:
         g = engine(name)
         g.set_option("msm_ba", rounds_g1)
         g.set_option("msm_ba_g2", rounds_g2)
+        g.set_option("ba_min_entries_g1", min_entries if min_entries else 1 << 18)      # the test MSMs are small: force the rounds on
+        g.set_option("ba_min_entries_g2", min_entries if min_entries else 1 << 18)
         for k, v in kw.items():
             g.set_option(k, v)
 
@@ -330,7 +332,10 @@ def test_batched_affine_rounds(rounds, m, G, gcd):
         _set_ba(rounds, rounds, ba_m=m, ba_g=G, ba_inv_gcd=gcd)
         _ba_body(orc, GENERATORS, dummy_r1cs, synthetic_r1cs)
     finally:
-        _set_ba(4, 5, ba_m=32, ba_g=16, ba_inv_gcd=1)   # the library defaults (Engine::Tune)
+        _set_ba(4, 5, ba_m=32, ba_g=16, ba_inv_gcd=1)   # the library defaults (Engine::Tune) ...
+        for name in ALL_CURVES:
+            engine(name).set_option("ba_min_entries_g1", 4 << 20)
+            engine(name).set_option("ba_min_entries_g2", 3 << 20)
 
 
 def _ba_body(orc, GENERATORS, dummy_r1cs, synthetic_r1cs):

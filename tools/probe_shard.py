@@ -1,12 +1,16 @@
-"""GPU probe of one rank of a `world`-way sharded proof on a single GPU: per-phase timings of g16_prove_partial."""
-import sys, time, os
+"""GPU probe of ONE rank of a `world`-way sharded proof on a single GPU (host-plumbed g16_prove_partial: no communicator
+needed): per-phase timings for a few launch geometries, and -- under `ncu --profile-from-start off` -- the launch list of one
+partial proof with the MSMs serialised.   python tools/probe_shard.py <curve> <log_n> <world> [tag]"""
+import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
+import torch
 from groth16_b200 import Groth16, _lib
 from groth16_b200.params import GENERATORS
 from groth16_b200.workload import synthetic_r1cs
 
 curve, log_n, world = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+tag = sys.argv[4] if len(sys.argv) > 4 else "probe"
 m, z, pub = synthetic_r1cs(curve, log_n, seed=1)
 g = Groth16(curve, 0)
 G = GENERATORS[g.curve.name]
@@ -14,12 +18,41 @@ pk = g.generate_parameters_with_qap(m, 11, 22, 33, 44, 55, G["g1"], G["g2"], exp
 g.load_proving_key(pk, 0, world)
 r = g.codec.fr.enc1(123456789)
 out = np.zeros(g.partial_limbs(), dtype=np.uint64)
-for flags in (0, _lib.SERIAL_MSMS):
+zd = torch.from_numpy(z.view(np.int64)).to("cuda:0")
+ON = _lib.ASSIGNMENT_ON_DEVICE
+lines = []
+for opts in ({}, {"msm_ba": 3}, {"msm_ba": 2}, {"msm_ba": 0}, {"msm_ba_g2": 3}, {"msm_ba_g2": 0}, {"msm_ba": 3, "msm_ba_g2": 3}, {"ba_g": 8}, {"ba_m": 8},
+             {"msm_ba": 0, "msm_ba_g2": 0}):
+    base = {"msm_ba": 4, "msm_ba_g2": 5, "ba_m": 32, "ba_g": 16}
+    base.update(opts)
+    for k, v in base.items():
+        g.set_option(k, v)
     for i in range(3):
-        t = time.time()
-        g.prove_partial_raw(r, z.ctypes.data, flags, out)
-        wall = (time.time() - t) * 1e3
-        tm = g.timings()
-        print(f"world={world} flags={flags} wall={wall:.2f}ms total={tm['total_ms']:.2f} h2d={tm['h2d_ms']:.2f} wm={tm['witness_map_ms']:.2f} "
-              f"msm={ {k: round(v,2) for k,v in tm['msm_ms'].items()} } accum={ {k: round(v,2) for k,v in tm['msm_accum_ms'].items()} } "
-              f"host={tm['host_finish_ms']:.2f} launches={tm['launches']}", flush=True)
+        g.prove_partial_raw(r, zd.data_ptr(), ON, out)
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    n = 10
+    for i in range(n):
+        g.prove_partial_raw(r, zd.data_ptr(), ON, out)
+    torch.cuda.synchronize()
+    wall = 1e3 * (time.perf_counter() - t) / n
+    tm = g.timings()
+    g.prove_partial_raw(r, zd.data_ptr(), ON | _lib.SERIAL_MSMS, out)
+    ts = g.timings()
+    line = {"world": world, "opts": opts, "wall_ms": round(wall, 3), "device_ms": round(tm["total_ms"], 3), "wm_ms": round(tm["witness_map_ms"], 3),
+            "host_ms": round(tm["host_finish_ms"], 3), "msm_ms_concurrent": {k: round(v, 2) for k, v in tm["msm_ms"].items()},
+            "msm_ms_serial": {k: round(v, 2) for k, v in ts["msm_ms"].items()}, "accum_ms_serial": {k: round(v, 2) for k, v in ts["msm_accum_ms"].items()},
+            "launches": tm["launches"], "entries": tm["msm_entries"]}
+    print(json.dumps(line), flush=True)
+    lines.append(line)
+for k, v in {"msm_ba": 4, "msm_ba_g2": 5, "ba_m": 32, "ba_g": 16}.items():
+    g.set_option(k, v)
+g.prove_partial_raw(r, zd.data_ptr(), ON | _lib.SERIAL_MSMS, out)
+torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStart()
+g.prove_partial_raw(r, zd.data_ptr(), ON | _lib.SERIAL_MSMS, out)
+torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStop()
+with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", f"{tag}_shard{world}.jsonl"), "w") as f:
+    for l in lines:
+        f.write(json.dumps(l) + "\n")

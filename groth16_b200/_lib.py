@@ -31,7 +31,7 @@ class Timings(C.Structure):
     _fields_ = [("total_ms", C.c_float), ("h2d_ms", C.c_float), ("witness_map_ms", C.c_float),
                 ("msm_ms", C.c_float * 5), ("msm_accum_ms", C.c_float * 5), ("host_finish_ms", C.c_float),
                 ("msm_pairs", C.c_uint64 * 5), ("msm_entries", C.c_uint64 * 5), ("launches", C.c_uint64),
-                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("msm_begin_ms", C.c_float * 5), ("msm_end_ms", C.c_float * 5)]
 
 
 class Config(C.Structure):

@@ -409,6 +409,8 @@ class Groth16:
                     msm_accum_ms={n: t.msm_accum_ms[i] for i, n in enumerate(names)},
                     msm_pairs={n: int(t.msm_pairs[i]) for i, n in enumerate(names)},
                     msm_entries={n: int(t.msm_entries[i]) for i, n in enumerate(names)},
+                    msm_begin_ms={n: t.msm_begin_ms[i] for i, n in enumerate(names)},
+                    msm_end_ms={n: t.msm_end_ms[i] for i, n in enumerate(names)},
                     host_finish_ms=t.host_finish_ms, launches=int(t.launches), h2d_bytes=int(t.h2d_bytes),
                     d2h_bytes=int(t.d2h_bytes))
 

@@ -289,6 +289,9 @@ struct Engine : IEngine {
     g.ba_occ = g2 ? tune.ba_occ_g2 : 0;
     return g;
   }
+  int wm_first_opt = 0;        // g16_set_option "wm_first": 1 / 0 / -1 = automatic (sharded keys).  Off: with enough hardware work
+                               // queues (CUDA_DEVICE_MAX_CONNECTIONS, see api.cu) the witness map is not held up, and delaying the
+                               // other accumulations then only idles the GPU (profiles/r02k_shard*.jsonl)
   bool share_b_sort = false;   // set when a key is made resident: b_g1_query and b_g2_query have the same identity pattern
   bool share_b_sort_wanted = true;
   void refresh_geoms() {   // after a knob changed: same shards, new launch geometry
@@ -352,6 +355,7 @@ struct Engine : IEngine {
     else if (k == "ba_min_entries_g1") tune.ba_min_g1 = std::max(0ll, v);
     else if (k == "ba_min_entries_g2") tune.ba_min_g2 = std::max(0ll, v);
     else if (k == "ntt_tma") { use_ntt_tma = v < 0 ? -1 : (v != 0 ? 1 : 0); return G16_OK; }
+    else if (k == "wm_first") { wm_first_opt = v < 0 ? -1 : (v ? 1 : 0); return G16_OK; }
     else if (k == "wm_split") { split_wm_wanted = v != 0; return G16_OK; }
     else if (k == "proof_slots") { proof_slots = v <= 1 ? 1 : NSLOTS; if (have_pk) decide_ba_memory(); return G16_OK; }
     // residency knobs: take effect at the NEXT g16_pk_load / g16_setup (they decide how many precomputed multiples a key keeps)
@@ -663,7 +667,7 @@ struct Engine : IEngine {
       G16_CUDA(cudaMemcpyAsync(ds.p, scalars, n * 32, cudaMemcpyHostToDevice, S0.st_main));
       G16_CUDA(msm_prepare_query<F>(S0.st_main, db.template as<Affine<F>>(), (uint32_t)n, 1, 0, dm.template as<uint8_t>()));
       const MsmGeom g = with_k0(msm_geom(n, FR_BITS, cfg_c, 0), sizeof(F) > 48);   // caller-supplied bases: no precomputed copies
-      cudaError_t e = msm_enqueue<F, Fr>(S0.st_main, ws, g, db.template as<Affine<F>>(), dm.template as<uint8_t>(), ds.template as<uint32_t>(), 1, false, &ctr, nullptr, nullptr, nullptr, nullptr);
+      cudaError_t e = msm_enqueue<F, Fr>(S0.st_main, ws, g, db.template as<Affine<F>>(), dm.template as<uint8_t>(), ds.template as<uint32_t>(), 1, false, &ctr, nullptr, nullptr, nullptr, nullptr, nullptr);
       if (e != cudaSuccess) { db.release(); ds.release(); dm.release(); return fail(G16_ERR_CUDA, std::string("msm_enqueue: ") + cudaGetErrorString(e)); }
       e = cudaStreamSynchronize(S0.st_main);
       db.release(); ds.release(); dm.release();
@@ -1013,9 +1017,13 @@ struct Engine : IEngine {
         // B in G1 and B in G2 run over the same scalars and identity pattern: one counting sort serves both.  B2 sorts
         // (its stream has the higher priority and its tail is the longest), B1 borrows the list.
         const bool share = share_b_sort && sl.run[M_B1] && sl.run[M_B2];
+        // "witness map first" (option, off by default): the MSMs that do not need h sort their entries at once but start
+        // accumulating only when the witness map is done, so that their register-heavy blocks do not slow the NTT kernels.
+        const bool wm_first = !sl.serial && (wm_first_opt > 0 || (wm_first_opt < 0 && world > 1));
+        cudaEvent_t gate = (wm_first && m != M_H) ? sl.ev_h : nullptr;
         if (m == M_B2 && share) { sl.b_sorted = MsmSorted{}; sl.b_sorted.ready = sl.ev_bsort; }
-        if (m == M_B2) e = msm_enqueue<Fq2, Fr>(st, sl.ws2, sl.geom[m], q[m].bases.template as<A2>(), q[m].mask.template as<uint8_t>(), sc, world, true, &ctr, sl.ev_a0[m], sl.ev_a1[m], share ? &sl.b_sorted : nullptr, nullptr);
-        else e = msm_enqueue<Fq, Fr>(st, sl.ws1[m], sl.geom[m], q[m].bases.template as<A1>(), q[m].mask.template as<uint8_t>(), sc, world, true, &ctr, sl.ev_a0[m], sl.ev_a1[m], nullptr, (m == M_B1 && share) ? &sl.b_sorted : nullptr);
+        if (m == M_B2) e = msm_enqueue<Fq2, Fr>(st, sl.ws2, sl.geom[m], q[m].bases.template as<A2>(), q[m].mask.template as<uint8_t>(), sc, world, true, &ctr, sl.ev_a0[m], sl.ev_a1[m], share ? &sl.b_sorted : nullptr, nullptr, gate);
+        else e = msm_enqueue<Fq, Fr>(st, sl.ws1[m], sl.geom[m], q[m].bases.template as<A1>(), q[m].mask.template as<uint8_t>(), sc, world, true, &ctr, sl.ev_a0[m], sl.ev_a1[m], nullptr, (m == M_B1 && share) ? &sl.b_sorted : nullptr, gate);
         if (e != cudaSuccess) return fail(G16_ERR_CUDA, std::string("msm_enqueue: ") + cudaGetErrorString(e));
       }
       G16_CUDA(cudaEventRecord(sl.ev_m1[m], st));
@@ -1071,7 +1079,9 @@ struct Engine : IEngine {
         cudaEventElapsedTime(&sl.tm.msm_accum_ms[m], sl.ev_a0[m], sl.ev_a1[m]);
         sl.tm.msm_entries[m] = m == M_B2 ? *sl.ws2.h_total : *sl.ws1[m].h_total;
       }
+      cudaEventElapsedTime(&sl.tm.msm_begin_ms[m], sl.ev_start, sl.ev_m0[m]);
       cudaEventElapsedTime(&ms, sl.ev_start, sl.ev_m1[m]);
+      sl.tm.msm_end_ms[m] = ms;
       if (ms > tot) tot = ms;
     }
     sl.tm.total_ms = tot;

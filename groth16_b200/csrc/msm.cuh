@@ -694,7 +694,8 @@ struct MsmSorted {
 template <class F, class FrF>
 cudaError_t msm_enqueue(cudaStream_t st, MsmWorkspace<F>& ws, const MsmGeom& g, const Affine<F>* d_bases,
                         const uint8_t* d_skip, const uint32_t* d_scalars, uint32_t scalar_stride, bool scalars_mont,
-                        MsmCounters* ctr, cudaEvent_t ev_acc0, cudaEvent_t ev_acc1, MsmSorted* lend, const MsmSorted* borrow) {
+                        MsmCounters* ctr, cudaEvent_t ev_acc0, cudaEvent_t ev_acc1, MsmSorted* lend, const MsmSorted* borrow,
+                        cudaEvent_t gate_accum) {
   cudaError_t e;
   if (g.n == 0) return cudaSuccess;
   if ((e = ws.prepare(g)) != cudaSuccess) return e;
@@ -741,6 +742,8 @@ cudaError_t msm_enqueue(cudaStream_t st, MsmWorkspace<F>& ws, const MsmGeom& g, 
   // batched-affine rounds: the (padded) sorted slots shrink 2^R-fold to a list of partial bucket sums (msm_ba.cuh)
   const Affine<F>* acc_bases = d_bases;
   const uint32_t* acc_sidx = sidx;
+  // optional gate between the sort and the accumulation (engine: "witness map first" schedule of small / sharded proofs)
+  if (gate_accum) cudaStreamWaitEvent(st, gate_accum, 0);
   if (ev_acc0) cudaEventRecord(ev_acc0, st);
   if (bp.R > 0) {
     Affine<F>* lists[2] = {ws.ba_l0.template as<Affine<F>>(), ws.ba_l1.template as<Affine<F>>()};
@@ -969,7 +972,7 @@ cudaError_t fb_batch_mul(cudaStream_t st, const Affine<F>& gen, const FrF* d_sca
 #define G16_MSM_TEMPLATES(X, F, FrF)                                                                                     \
   X cudaError_t msm_enqueue<F, FrF>(cudaStream_t, MsmWorkspace<F>&, const MsmGeom&, const Affine<F>*, const uint8_t*,    \
                                     const uint32_t*, uint32_t, bool, MsmCounters*, cudaEvent_t, cudaEvent_t, MsmSorted*, \
-                                    const MsmSorted*);                                                                   \
+                                    const MsmSorted*, cudaEvent_t);                                                      \
   X cudaError_t msm_prepare_query<F>(cudaStream_t, Affine<F>*, uint32_t, int, int, uint8_t*);                            \
   X cudaError_t fb_batch_mul<F, FrF>(cudaStream_t, const Affine<F>&, const FrF*, uint64_t, Affine<F>*, XYZZ<F>*);
 

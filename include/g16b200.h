@@ -189,6 +189,8 @@ typedef struct {
                               of the batched-affine rounds, < 2 %) = point additions of the accumulation stage     */
   uint64_t launches;     /* kernels launched by the last call                                                     */
   uint64_t h2d_bytes, d2h_bytes;
+  float msm_begin_ms[5]; /* start / end of each MSM's stream work, measured from the first enqueue of the proof: the       */
+  float msm_end_ms[5];   /* concurrent timeline of the five streams (h, l, a, b_g1, b_g2)                                  */
 } g16_timings;
 int g16_get_timings(const g16_ctx* ctx, g16_timings* out);
 

@@ -77,6 +77,8 @@ pub struct g16_timings {
     pub launches: u64,
     pub h2d_bytes: u64,
     pub d2h_bytes: u64,
+    pub msm_begin_ms: [f32; 5],
+    pub msm_end_ms: [f32; 5],
 }
 
 #[repr(C)]

@@ -21,9 +21,9 @@ out = np.zeros(g.partial_limbs(), dtype=np.uint64)
 zd = torch.from_numpy(z.view(np.int64)).to("cuda:0")
 ON = _lib.ASSIGNMENT_ON_DEVICE
 lines = []
-for opts in ({}, {"msm_ba": 3}, {"msm_ba": 2}, {"msm_ba": 0}, {"msm_ba_g2": 3}, {"msm_ba_g2": 0}, {"msm_ba": 3, "msm_ba_g2": 3}, {"ba_g": 8}, {"ba_m": 8},
-             {"msm_ba": 0, "msm_ba_g2": 0}):
-    base = {"msm_ba": 4, "msm_ba_g2": 5, "ba_m": 32, "ba_g": 16}
+GRID = json.loads(os.environ["G16_PROBE_GRID"]) if os.environ.get("G16_PROBE_GRID") else [{}, {"msm_ba": 0, "msm_ba_g2": 0}]
+for opts in GRID:
+    base = {"msm_ba": 4, "msm_ba_g2": 5, "ba_m": 32, "ba_g": 16, "ba_min_entries_g1": 4 << 20, "ba_min_entries_g2": 3 << 20, "wm_first": -1}
     base.update(opts)
     for k, v in base.items():
         g.set_option(k, v)
@@ -42,10 +42,11 @@ for opts in ({}, {"msm_ba": 3}, {"msm_ba": 2}, {"msm_ba": 0}, {"msm_ba_g2": 3}, 
     line = {"world": world, "opts": opts, "wall_ms": round(wall, 3), "device_ms": round(tm["total_ms"], 3), "wm_ms": round(tm["witness_map_ms"], 3),
             "host_ms": round(tm["host_finish_ms"], 3), "msm_ms_concurrent": {k: round(v, 2) for k, v in tm["msm_ms"].items()},
             "msm_ms_serial": {k: round(v, 2) for k, v in ts["msm_ms"].items()}, "accum_ms_serial": {k: round(v, 2) for k, v in ts["msm_accum_ms"].items()},
-            "launches": tm["launches"], "entries": tm["msm_entries"]}
+            "launches": tm["launches"], "entries": tm["msm_entries"],
+            "timeline_begin": {k: round(v, 2) for k, v in tm["msm_begin_ms"].items()}, "timeline_end": {k: round(v, 2) for k, v in tm["msm_end_ms"].items()}}
     print(json.dumps(line), flush=True)
     lines.append(line)
-for k, v in {"msm_ba": 4, "msm_ba_g2": 5, "ba_m": 32, "ba_g": 16}.items():
+for k, v in {"msm_ba": 4, "msm_ba_g2": 5, "ba_m": 32, "ba_g": 16, "ba_min_entries_g1": 4 << 20, "ba_min_entries_g2": 3 << 20}.items():
     g.set_option(k, v)
 g.prove_partial_raw(r, zd.data_ptr(), ON | _lib.SERIAL_MSMS, out)
 torch.cuda.synchronize()

@@ -50,9 +50,8 @@ def parse():
                          "(benches/bench.rs:17-20,41-64): constant witness, a/b queries almost all identity")
     ap.add_argument("--inflight", type=int, default=0, choices=[0, 1, 2],
                     help="proofs in flight per GPU: 1 = one proof at a time; 2 = software pipeline over the two proof slots of a "
-                         "context (g16_prove_submit / g16_prove_wait); 0 (default) = 1 on one GPU (a single proof with five MSM "
-                         "streams already saturates the multiplier pipes) and 2 for the sharded multi-GPU proof (per-rank work is "
-                         "small there, the second proof fills the latency-bound tails and hides the NCCL gather)")
+                         "context (g16_prove_submit / g16_prove_wait); 0 (default) = 2 up to 2^20 constraints (the next proof fills "
+                         "the latency-bound tail of the previous one; single-proof latency is reported next to it), 1 above")
     ap.add_argument("--mode", default="auto", choices=["auto", "shard", "replicas"],
                     help="N > 1: 'shard' splits every MSM of ONE proof over the GPUs (strong scaling, NCCL gather of partial "
                          "points) and is what `value` reports; 'replicas' lets every GPU prove its own proofs (weak scaling, no "
@@ -73,16 +72,25 @@ def workload_name(a):
 
 # ------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).
+
+    The nvidia-smi process is started BEFORE the warm-up steps: its start-up (process spawn, NVML attaching to every GPU of
+    the box) takes driver-wide locks for hundreds of milliseconds, which inside a 0.3 s timed region of an 8-GPU sharded
+    run stalled kernel launches on all ranks (profiles/r02_bench_h_bls12_381_20_n8.json: `value` 77 proofs/s under the
+    sampler against 137 for the unsampled host-input run of the same process).  Every sample is stamped on arrival and only
+    those that fall between mark_begin() and mark_end() are reported."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device_index):
         self.idx = device_index
         self.proc = None
-        self.lines = []
+        self.lines = []          # (arrival time, text)
+        self.t_begin = self.t_end = None
 
     def start(self):
+        if self.proc:
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -93,19 +101,39 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.perf_counter(), ln.strip()))
+
+    def wait_ready(self, timeout=5.0):
+        """block until the first sample has arrived (nvidia-smi is past its start-up)"""
+        t = time.perf_counter()
+        while self.proc and not self.lines and time.perf_counter() - t < timeout:
+            time.sleep(0.02)
+
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
+
+    def mark_end(self):
+        self.t_end = time.perf_counter()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.15)   # the sample taken at the end of the region is printed up to one period later
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        self.proc = None
+        t0 = self.t_begin if self.t_begin is not None else 0.0
+        t1 = (self.t_end if self.t_end is not None else time.perf_counter()) + 0.12
+        inside = [ln for t, ln in self.lines if t0 <= t <= t1]
+        window = "timed region"
+        if not inside:   # region shorter than one sampling period: the nearest samples (warm-up steps: same load)
+            inside = [ln for _, ln in self.lines[-3:]]
+            window = "nearest samples (timed region shorter than the 100 ms sampling period)"
         sm, smax, reasons, pw = [], [], set(), []
-        for ln in self.lines:
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -119,7 +147,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "power_w_max": max(pw), "samples": len(sm),
-                "reasons": sorted(reasons)}
+                "window": window, "reasons": sorted(reasons)}
 
 
 def host_threads(requested=0):
@@ -382,13 +410,15 @@ def run_cuda(a):
                 dist.barrier()
             torch.cuda.synchronize()
             if sampler:
-                sampler.start()
+                sampler.mark_begin()
             t0 = time.perf_counter()
             dev_ms, launches = self.run_steps(zptr, flags, steps)
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
             dt = time.perf_counter() - t0
+            if sampler:
+                sampler.mark_end()
             clocks = sampler.stop() if sampler else None
             if world > 1:
                 tt = torch.tensor([dt], dtype=torch.float64, device=dev)
@@ -409,13 +439,17 @@ def run_cuda(a):
 
         def measure(self, units, sampler=None):
             """warm-up, resident-input run, single-proof latency, host-input (e2e) run"""
-            for _ in range(max(a.warmup, 3)):
-                self.step(z_dev.data_ptr(), ON_DEV)
+            if sampler:
+                sampler.start()   # before the warm-up: nvidia-smi's start-up must not fall into the timed region
+                sampler.wait_ready()
+            # warm-up through the SAME path as the timed steps: with two proofs in flight the second proof slot's workspaces
+            # (GBs of cudaMalloc) are allocated on first use -- in round-2 records taken before this fix that happened inside
+            # the first timed region (`value` of the inflight-2 runs was understated; their `e2e` run came after and was not)
+            self.run_steps(z_dev.data_ptr(), ON_DEV, max(a.warmup, 3))
             first = self.step(z_dev.data_ptr(), ON_DEV).copy()
             dt, dev_ms, launches, clocks = self.timed(z_dev.data_ptr(), ON_DEV, a.steps, sampler)
             lat = self.latency(z_dev.data_ptr(), ON_DEV)
-            for _ in range(2):
-                self.step(z_pinned.data_ptr(), 0)
+            self.run_steps(z_pinned.data_ptr(), 0, 2)
             assert np.array_equal(first, proof), "resident-input and host-input proofs differ"
             dt_e, _, _, _ = self.timed(z_pinned.data_ptr(), 0, a.steps)
             tm_e = g.timings()
@@ -427,8 +461,13 @@ def run_cuda(a):
 
     sampler = ClockSampler(local) if rank == 0 else None
     secondary = None
+    # Two proofs in flight (software pipeline over the two proof slots of a context) up to 2^20: the next proof's sort and
+    # first rounds fill the latency-bound tail of the previous one (bucket reduction, host finish) -- +3.7 % on one GPU
+    # (gpurun_out/bench_r02p_*.json: 35.8 vs 34.5 proofs/s), more on the small per-rank shards.  Larger circuits keep one proof
+    # in flight: the second slot's work lists would compete with the precomputed multiples for HBM.
+    auto_inflight = 1 if (big or a.log_n > 20) else 2
     if want_shard:
-        arm = Arm("shard", a.inflight or (1 if big else 2))
+        arm = Arm("shard", a.inflight or auto_inflight)
         main = arm.measure(1, sampler)
         par = (f"msm-shard{world}: one proof per step, pair i of every MSM on rank i mod {world}, witness map replicated, "
                "3 partial points per rank (768 B) all-gathered by ONE ncclAllGather issued inside the library "
@@ -436,13 +475,13 @@ def run_cuda(a):
         scaling = "strong"
         if a.mode == "auto" and not big:
             g.load_proving_key(pk, 0, 1)          # full key resident again: every rank proves on its own
-            rep = Arm("single", a.inflight or 1).measure(world)
+            rep = Arm("single", a.inflight or auto_inflight).measure(world)
             assert np.array_equal(rep["proof"], main["proof"]), "sharded and single-GPU proofs differ"
             secondary = {"mode": f"replicas{world}: one independent proof per GPU per step, no communication", "scaling": "weak",
                          "value": rep["value"], "unit": "proofs/s", "ms_per_step": rep["ms_per_step"], "e2e_value": rep["e2e"]["value"],
                          "proof_equals_sharded_proof": True}
     else:
-        arm = Arm("single", a.inflight or 1)
+        arm = Arm("single", a.inflight or auto_inflight)
         main = arm.measure(world, sampler)
         par = f"replicas{world} (one independent proof per GPU per step, no communication)" if world > 1 else "single-gpu"
         scaling = "weak" if world > 1 else "strong"
@@ -524,9 +563,10 @@ def run_cuda(a):
                              "sorted digit arrays (134 MB per MSM) are streamed every step",
                        "timing": "wall clock around K complete proofs bracketed by barrier+synchronize (host finish/assembly "
                                  "included), max over ranks; with inflight=2 proof i+1 is submitted before proof i is waited "
-                                 "for (two proof slots per context); device_ms_per_step = CUDA-event span of one proof's GPU "
-                                 "work; latency_ms_single_proof = one proof at a time"},
-            "device_ms_per_step": main["device_ms_per_step"],
+                                 "for (two proof slots per context); device_span_ms_per_proof = CUDA-event span of one proof's "
+                                 "GPU work (with two proofs in flight the spans of successive proofs overlap, so it is about "
+                                 "twice ms_per_step); latency_ms_single_proof = one proof at a time"},
+            "device_span_ms_per_proof": main["device_ms_per_step"],
             "latency_ms_single_proof": main["latency_ms_single_proof"],
             "e2e": main["e2e"],
             "gpu_launches": main["launches"],

@@ -249,7 +249,10 @@ struct Engine : IEngine {
     int k0_g1 = 0;        // sorted entries per accumulation thread (0 = automatic)
     int k0_g2 = 0;
     int acc_block = 128;
-    int ba_occ_g2 = 0;    // 3: Fq2 batched-affine kernels compiled for 3 resident blocks per SM (168 registers, spills)
+    int ba_occ_g2 = 0;    // != 0: register-lean Fq2 round kernels, 3 resident blocks per SM (168 registers; msm_ba.cuh)
+    int ba_occ_g1 = 0;    // != 0: register-lean G1 round kernels, 5 resident blocks per SM
+    int ba_cap_fwd_g1 = 0, ba_cap_bwd_g1 = 0;   // blocks per SM of a forward / backward round launch (0 = one block per tile)
+    int ba_cap_fwd_g2 = 0, ba_cap_bwd_g2 = 0;
     // The rounds cost ~0.12 ms of latency each (forward / combine / backward launches, one inversion per combine lane) and save
     // ~0.10 ns per G1 entry, ~0.35 ns per G2 entry: below these entry counts (the per-rank shards of an 8-way proof have 2.1 M /
     // 1.1 M) the plain XYZZ accumulation is faster (profiles/r02g_shard8.jsonl: 8.8 vs 10.9 ms per sharded step).
@@ -286,7 +289,9 @@ struct Engine : IEngine {
     g.ba_G = tune.ba_G;
     g.ba_gcd = tune.ba_gcd;
     g.acc_block = tune.acc_block;
-    g.ba_occ = g2 ? tune.ba_occ_g2 : 0;
+    g.ba_occ = g2 ? tune.ba_occ_g2 : tune.ba_occ_g1;
+    g.ba_grid_fwd = sm_count * (g2 ? tune.ba_cap_fwd_g2 : tune.ba_cap_fwd_g1);
+    g.ba_grid_bwd = sm_count * (g2 ? tune.ba_cap_bwd_g2 : tune.ba_cap_bwd_g1);
     return g;
   }
   int wm_first_opt = 0;        // g16_set_option "wm_first": 1 / 0 / -1 = automatic (sharded keys).  Off: with enough hardware work
@@ -351,7 +356,12 @@ struct Engine : IEngine {
     else if (k == "acc_k0_g1") tune.k0_g1 = (int)v;
     else if (k == "acc_k0_g2") tune.k0_g2 = (int)v;
     else if (k == "acc_block") tune.acc_block = (int)v;
-    else if (k == "ba_occ_g2") tune.ba_occ_g2 = v == 3 ? 3 : 0;
+    else if (k == "ba_occ_g2") tune.ba_occ_g2 = v != 0 ? 3 : 0;
+    else if (k == "ba_occ_g1") tune.ba_occ_g1 = v != 0 ? 5 : 0;
+    else if (k == "ba_cap_fwd_g1") tune.ba_cap_fwd_g1 = (int)std::max(0ll, std::min(v, 16ll));
+    else if (k == "ba_cap_bwd_g1") tune.ba_cap_bwd_g1 = (int)std::max(0ll, std::min(v, 16ll));
+    else if (k == "ba_cap_fwd_g2") tune.ba_cap_fwd_g2 = (int)std::max(0ll, std::min(v, 16ll));
+    else if (k == "ba_cap_bwd_g2") tune.ba_cap_bwd_g2 = (int)std::max(0ll, std::min(v, 16ll));
     else if (k == "ba_min_entries_g1") tune.ba_min_g1 = std::max(0ll, v);
     else if (k == "ba_min_entries_g2") tune.ba_min_g2 = std::max(0ll, v);
     else if (k == "ntt_tma") { use_ntt_tma = v < 0 ? -1 : (v != 0 ? 1 : 0); return G16_OK; }
@@ -378,6 +388,7 @@ struct Engine : IEngine {
     o->ba_m = tune.ba_m; o->ba_g = tune.ba_G; o->ba_inv_gcd = tune.ba_gcd; o->acc_block = tune.acc_block;
     o->sm_count = sm_count;
     o->world = (int32_t)world; o->rank = (int32_t)rank;
+    o->ba_lean_g1 = g1.ba_occ != 0; o->ba_lean_g2 = g2.ba_occ != 0;
     return G16_OK;
   }
   template <class F>
@@ -420,6 +431,11 @@ struct Engine : IEngine {
     env_int("G16_ACC_K0_G2", tune.k0_g2, 4, 1024);
     env_int("G16_ACC_BLOCK", tune.acc_block, 32, 128);
     env_int("G16_BA_OCC_G2", tune.ba_occ_g2, 0, 3);
+    env_int("G16_BA_OCC_G1", tune.ba_occ_g1, 0, 5);
+    env_int("G16_BA_CAP_FWD_G1", tune.ba_cap_fwd_g1, 0, 16);
+    env_int("G16_BA_CAP_BWD_G1", tune.ba_cap_bwd_g1, 0, 16);
+    env_int("G16_BA_CAP_FWD_G2", tune.ba_cap_fwd_g2, 0, 16);
+    env_int("G16_BA_CAP_BWD_G2", tune.ba_cap_bwd_g2, 0, 16);
     if (cfg_c < 0 || cfg_c > 24) cfg_c = 0;
     // Stream priorities (greatest first): the witness map (H's MSM waits for it), then the G2 MSM (longest latency-bound
     // tail: its point additions cost ~3x a G1 addition), then H (starts last), then L / A / B-in-G1.  The heavy

@@ -203,10 +203,11 @@ typedef struct {
   int32_t ba_m, ba_g, ba_inv_gcd;     /* additions per thread and round; products per inversion; 1 = safegcd      */
   int32_t acc_block, sm_count;
   int32_t rank, world;
-  int32_t reserved[4];
+  int32_t ba_lean_g1, ba_lean_g2;     /* != 0: register-lean round kernels (more resident warps per SM)           */
+  int32_t reserved[2];
 } g16_config;
 int g16_get_config(const g16_ctx* ctx, g16_config* out);
-/* key: "msm_ba", "msm_ba_g2", "ba_m", "ba_g", "ba_inv_gcd", "acc_k0_g1", "acc_k0_g2", "acc_block", "share_b_sort", "ba_occ_g2",
+/* key: "msm_ba", "msm_ba_g2", "ba_m", "ba_g", "ba_inv_gcd", "acc_k0_g1", "acc_k0_g2", "acc_block", "share_b_sort", "ba_occ_g1", "ba_occ_g2",
  * "ba_min_entries_g1", "ba_min_entries_g2" (smallest MSM, in bucket entries, that runs the rounds), "ntt_tma", "wm_split", "proof_slots", and -- effective at the next
  * g16_pk_load / g16_setup -- "msm_ne", "msm_c", "msm_maxcopies" (the G16_* environment
  * variables of INTEGRATION.md section 6, read once at g16_ctx_create, in lower case without the prefix).  Takes effect

@@ -158,7 +158,7 @@ def test_batched_affine_rounds_host(tmp_path):
                            os.path.join(ROOT, "tests", "host", "ba_check.cu")])
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert "18 cases, 0 mismatches" in out.stdout
+    assert "24 cases, 0 mismatches" in out.stdout
 
 
 def test_prepare_inputs_host_logic():

@@ -253,11 +253,17 @@ struct Engine : IEngine {
     int ba_occ_g1 = 0;    // != 0: register-lean G1 round kernels, 5 resident blocks per SM
     int ba_cap_fwd_g1 = 0, ba_cap_bwd_g1 = 0;   // blocks per SM of a forward / backward round launch (0 = one block per tile)
     int ba_cap_fwd_g2 = 0, ba_cap_bwd_g2 = 0;
-    // The rounds cost ~0.12 ms of latency each (forward / combine / backward launches, one inversion per combine lane) and save
-    // ~0.10 ns per G1 entry, ~0.35 ns per G2 entry: below these entry counts (the per-rank shards of an 8-way proof have 2.1 M /
-    // 1.1 M) the plain XYZZ accumulation is faster (profiles/r02g_shard8.jsonl: 8.8 vs 10.9 ms per sharded step).
-    long long ba_min_g1 = 4ll << 20;
-    long long ba_min_g2 = 3ll << 20;
+    // Smallest MSM (in bucket entries) that runs the rounds, and how many: a round halves a list whose buckets hold
+    // `entries / buckets` slots on average and pads every bucket to 2^R slots, so R is the smallest value with
+    // 11 * 2^R >= that average, capped by ba_g1 / ba_g2 (4 / 5 at
+    // 2^20 pairs on one GPU, 3 on the 2.1 M-entry shards of an 8-way proof, 2 on its 1.0 M-entry A / B shards).  Round 2
+    // first kept the plain XYZZ accumulation below 4 M entries because one proof at a time is latency-bound there
+    // (profiles/r02g_shard8.jsonl); with two proofs in flight -- how the sharded arm runs -- the rounds' smaller
+    // multiplier footprint wins: 8.64 -> 7.37 ms per 8-way shard, 11.03 -> 10.73 ms per 4-way shard, and the
+    // one-at-a-time latency does not lose either (8.86 -> 8.46 ms; profiles/r02q_shard*.jsonl).
+    long long ba_min_g1 = 1ll << 19;
+    long long ba_min_g2 = 1ll << 19;
+    int ba_adaptive = 1;  // 0: exactly ba_g1 / ba_g2 rounds whatever the bucket occupancy (tests)
   } tune;
   MsmGeom pick_geom(uint64_t cnt) const {
     if (cfg_ne <= 0) return msm_geom(cnt, FR_BITS, cfg_c, 0);
@@ -284,7 +290,10 @@ struct Engine : IEngine {
     const int r = g2 ? tune.ba_g2 : tune.ba_g1;
     const bool allowed = ba_allowed && (m < 0 || ((ba_allowed_mask >> m) & 1));
     const uint64_t min_entries = (uint64_t)std::max(1ll << 18, g2 ? tune.ba_min_g2 : tune.ba_min_g1);
-    g.ba = (allowed && r > 0 && g.max_entries >= min_entries) ? std::min(r, (int)MSM_BA_MAX_ROUNDS) : 0;
+    int r_fit = 0;   // smallest R with 11 * 2^R >= average entries per bucket
+    for (uint64_t per_bucket = g.max_entries / std::max<uint64_t>(1, g.nkeys); (11ull << r_fit) < per_bucket; r_fit++) {}
+    if (!tune.ba_adaptive) r_fit = r;
+    g.ba = (allowed && r > 0 && g.max_entries >= min_entries) ? std::min(std::min(r, r_fit), (int)MSM_BA_MAX_ROUNDS) : 0;
     g.ba_m = tune.ba_m;
     g.ba_G = tune.ba_G;
     g.ba_gcd = tune.ba_gcd;
@@ -362,6 +371,7 @@ struct Engine : IEngine {
     else if (k == "ba_cap_bwd_g1") tune.ba_cap_bwd_g1 = (int)std::max(0ll, std::min(v, 16ll));
     else if (k == "ba_cap_fwd_g2") tune.ba_cap_fwd_g2 = (int)std::max(0ll, std::min(v, 16ll));
     else if (k == "ba_cap_bwd_g2") tune.ba_cap_bwd_g2 = (int)std::max(0ll, std::min(v, 16ll));
+    else if (k == "ba_adaptive") tune.ba_adaptive = v ? 1 : 0;
     else if (k == "ba_min_entries_g1") tune.ba_min_g1 = std::max(0ll, v);
     else if (k == "ba_min_entries_g2") tune.ba_min_g2 = std::max(0ll, v);
     else if (k == "ntt_tma") { use_ntt_tma = v < 0 ? -1 : (v != 0 ? 1 : 0); return G16_OK; }

@@ -208,7 +208,8 @@ typedef struct {
 } g16_config;
 int g16_get_config(const g16_ctx* ctx, g16_config* out);
 /* key: "msm_ba", "msm_ba_g2", "ba_m", "ba_g", "ba_inv_gcd", "acc_k0_g1", "acc_k0_g2", "acc_block", "share_b_sort", "ba_occ_g1", "ba_occ_g2",
- * "ba_min_entries_g1", "ba_min_entries_g2" (smallest MSM, in bucket entries, that runs the rounds), "ntt_tma", "wm_split", "proof_slots", and -- effective at the next
+ * "ba_min_entries_g1", "ba_min_entries_g2" (smallest MSM, in bucket entries, that runs the rounds), "ba_adaptive" (0 = exactly
+ * "msm_ba" rounds, 1 = at most that many, fewer for sparsely filled buckets), "ba_cap_fwd_g1", "ba_cap_bwd_g1", "ba_cap_fwd_g2", "ba_cap_bwd_g2", "ntt_tma", "wm_split", "proof_slots", and -- effective at the next
  * g16_pk_load / g16_setup -- "msm_ne", "msm_c", "msm_maxcopies" (the G16_* environment
  * variables of INTEGRATION.md section 6, read once at g16_ctx_create, in lower case without the prefix).  Takes effect
  * from the next proof; results never depend on these knobs. */

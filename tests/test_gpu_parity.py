@@ -317,30 +317,35 @@ def _set_ba(rounds_g1, rounds_g2, min_entries=0, **kw):
         g.set_option("msm_ba_g2", rounds_g2)
         g.set_option("ba_min_entries_g1", min_entries if min_entries else 1 << 18)      # the test MSMs are small: force the rounds on
         g.set_option("ba_min_entries_g2", min_entries if min_entries else 1 << 18)
+        g.set_option("ba_adaptive", 0)                                                    # exactly these many rounds
         for k, v in kw.items():
             g.set_option(k, v)
 
 
 @pytest.mark.parametrize("rounds,m,G,gcd,lean", [(0, 16, 64, 1, 0), (1, 4, 7, 0, 0), (3, 32, 64, 1, 0), (6, 16, 16, 1, 0),
-                                                 (4, 32, 16, 1, 1), (2, 5, 3, 0, 1)])
+                                                 (4, 32, 16, 1, 1), (2, 5, 3, 0, 1), (3, 8, 16, 1, 2)])
 def test_batched_affine_rounds(rounds, m, G, gcd, lean):
     """The batched-affine pre-reduction (csrc/msm_ba.cuh; default: 4 rounds on G1 MSMs; g16_set_option "msm_ba" /
     "msm_ba_g2") must not change a single bit whatever the number of rounds (0 = plain XYZZ accumulation), the additions
-    per thread, the products per inversion, the inversion routine or the kernel build (lean = the register-lean round
-    kernels, "ba_occ_g1" / "ba_occ_g2"): skewed G1 MSM with repeated bases, a 2^14-point G2
+    per thread, the products per inversion, the inversion routine or the kernel build (lean = 1: the register-lean round
+    kernels, "ba_occ_g1" / "ba_occ_g2"; lean = 2: capped grids pulling tiles from a counter, "ba_cap_*"): skewed G1 MSM with repeated bases, a 2^14-point G2
     MSM, and full proofs (synthetic 2^14, and the degenerate DummyCircuit where every scalar is equal) against the CPU
     oracle."""
     import orc
     from groth16_b200.params import GENERATORS
     from groth16_b200.workload import dummy_r1cs, synthetic_r1cs
     try:
-        _set_ba(rounds, rounds, ba_m=m, ba_g=G, ba_inv_gcd=gcd, ba_occ_g1=lean, ba_occ_g2=lean)
+        cap = 1 if lean == 2 else 0
+        _set_ba(rounds, rounds, ba_m=m, ba_g=G, ba_inv_gcd=gcd, ba_occ_g1=int(lean == 1), ba_occ_g2=int(lean == 1),
+                ba_cap_fwd_g1=cap, ba_cap_bwd_g1=cap, ba_cap_fwd_g2=cap, ba_cap_bwd_g2=cap)
         _ba_body(orc, GENERATORS, dummy_r1cs, synthetic_r1cs)
     finally:
-        _set_ba(4, 5, ba_m=32, ba_g=16, ba_inv_gcd=1, ba_occ_g1=LEAN_DEFAULT[0], ba_occ_g2=LEAN_DEFAULT[1])   # the library defaults (Engine::Tune) ...
+        _set_ba(4, 5, ba_m=32, ba_g=16, ba_inv_gcd=1, ba_occ_g1=LEAN_DEFAULT[0], ba_occ_g2=LEAN_DEFAULT[1],
+                ba_cap_fwd_g1=0, ba_cap_bwd_g1=0, ba_cap_fwd_g2=0, ba_cap_bwd_g2=0)   # the library defaults (Engine::Tune) ...
         for name in ALL_CURVES:
-            engine(name).set_option("ba_min_entries_g1", 4 << 20)
-            engine(name).set_option("ba_min_entries_g2", 3 << 20)
+            engine(name).set_option("ba_min_entries_g1", 1 << 19)
+            engine(name).set_option("ba_min_entries_g2", 1 << 19)
+            engine(name).set_option("ba_adaptive", 1)
 
 
 def _ba_body(orc, GENERATORS, dummy_r1cs, synthetic_r1cs):

@@ -60,6 +60,7 @@ def main():
     cols = [("gpu__time_duration.sum", "ms"), ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm%"),
             ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue%"), ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps%"),
             ("launch__registers_per_thread", "regs"), ("dram__bytes_read.sum", "dramR"), ("dram__bytes_write.sum", "dramW"),
+            ("dram__bytes.sum.per_second", "dramTB/s"), ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram%"),
             ("lts__t_sector_hit_rate.pct", "L2hit%"),
             ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "st_wait"),
             ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "st_long"),
@@ -74,6 +75,18 @@ def main():
         v = float(v.replace(",", ""))
         return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
 
+    def dur_ms(row):
+        return float(row[ix["gpu__time_duration.sum"]].replace(",", "")) * {"us": 1e-3, "usecond": 1e-3, "ns": 1e-6, "s": 1e3}.get(units[ix["gpu__time_duration.sum"]], 1)
+
+    def dram_bytes(row):
+        """dram__bytes_read.sum + dram__bytes_write.sum; the section-based capture (no --set full) only carries the rate:
+        dram__bytes.sum.per_second x gpu__time_duration.sum"""
+        if "dram__bytes_read.sum" in ix:
+            return to_bytes(row[ix["dram__bytes_read.sum"]], units[ix["dram__bytes_read.sum"]]) + to_bytes(row[ix["dram__bytes_write.sum"]], units[ix["dram__bytes_write.sum"]])
+        k = "dram__bytes.sum.per_second"
+        rate = float(row[ix[k]].replace(",", "")) * {"byte/s": 1, "Kbyte/s": 1e3, "Mbyte/s": 1e6, "Gbyte/s": 1e9, "Tbyte/s": 1e12}[units[ix[k]]]
+        return rate * dur_ms(row) * 1e-3
+
     for row in rd:
         n = short(row[ix["Kernel Name"]])
         seen[n] += 1
@@ -82,7 +95,7 @@ def main():
             if n in ("ba_forward_kernel<Fq>", "ba_forward_kernel<Fq, 0>") and not stage["on"] and seen[n] == 1:
                 stage["on"] = True
             if stage["on"] and (n.startswith("ba_") or n.startswith("msm_accum_l0")) and "Fq2" not in n:
-                stage["dram"] += to_bytes(row[ix["dram__bytes_read.sum"]], units[ix["dram__bytes_read.sum"]]) + to_bytes(row[ix["dram__bytes_write.sum"]], units[ix["dram__bytes_write.sum"]])
+                stage["dram"] += dram_bytes(row)
                 stage["ms"] += float(row[ix["gpu__time_duration.sum"]].replace(",", "")) * (1e-3 if units[ix["gpu__time_duration.sum"]] in ("us", "usecond") else 1)
                 if n.startswith("msm_accum_l0"):
                     stage["done"] = True

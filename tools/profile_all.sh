@@ -9,7 +9,8 @@
 #   <tag>_meta.json         kernel_rev + library configuration of the capture
 # Never read a bench number from these runs.
 set -u
-TAG=${1:-r02}; CURVE=${2:-bls12_381}; LOGN=${3:-20}; shift 3 2>/dev/null
+TAG=${1:-r02}; CURVE=${2:-bls12_381}; LOGN=${3:-20}
+if [ $# -ge 3 ]; then shift 3; else shift $#; fi
 O=gpurun_out; mkdir -p $O
 export G16_PROFILE_TAG=$TAG
 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file $O/${TAG}_launches.csv \

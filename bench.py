@@ -469,7 +469,9 @@ def run_cuda(a):
     if want_shard:
         arm = Arm("shard", a.inflight or auto_inflight)
         main = arm.measure(1, sampler)
-        par = (f"msm-shard{world}: one proof per step, pair i of every MSM on rank i mod {world}, witness map replicated, "
+        main["library"] = g.config()              # launch geometry of this rank's shard (before the replicas reload the full key)
+        par = (f"msm-shard{world}: one proof per step, pair i of every MSM on rank i mod {world}, the witness map's three a/b/c chains spread over the "
+               "ranks (ncclSend/Recv, h broadcast), "
                "3 partial points per rank (768 B) all-gathered by ONE ncclAllGather issued inside the library "
                "(g16_prove_sharded), every rank finishes the same proof")
         scaling = "strong"
@@ -509,7 +511,9 @@ def run_cuda(a):
             peak, peak_src = measured_peak_hbm()
             summ = ncu_summary() or {}
             cfg = g.config()
-            same_code = summ.get("kernel_rev") == kernel_rev() and summ.get("config") == cfg
+            # the capture describes ONE workload: same kernel sources, same launch geometry, same curve / size / circuit
+            same_code = (summ.get("kernel_rev") == kernel_rev() and summ.get("config") == cfg and summ.get("curve") == a.curve
+                         and summ.get("log_n") == a.log_n and summ.get("workload", "synthetic") == a.workload)
             ach = b_g1 / (t_g1 * 1e-3) / 1e9 if t_g1 > 0 else 0.0
             # honest bound: the integer-multiply pipe.  IMAD.WIDE per bucket entry from the SASS (cuobjdump)
             nl = 2 * nq                          # 32-bit limbs of Fq
@@ -558,7 +562,7 @@ def run_cuda(a):
             "vs_baseline": None,
             "dtype": "u32 limbs (255-bit Fr / 381-bit Fq Montgomery integers)", "data": "synthetic",
             "config": {"workload": workload_name(a), "curve": a.curve, "log_n": a.log_n, "parallelism": par,
-                       "inflight": main["inflight"], "library": g.config(),
+                       "inflight": main["inflight"], "library": main.get("library") or g.config(),
                        "l2": "inputs exceed L2: resident proving key with precomputed multiples (GBs) + 32 MiB assignment + "
                              "sorted digit arrays (134 MB per MSM) are streamed every step",
                        "timing": "wall clock around K complete proofs bracketed by barrier+synchronize (host finish/assembly "

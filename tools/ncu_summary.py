@@ -110,7 +110,8 @@ def main():
     meta_p = os.path.join(O, f"{tag}_meta.json")
     meta = json.load(open(meta_p)) if os.path.exists(meta_p) else {}
     summ = {"source": f"profiles/{tag}_ncu_full_raw.csv (ncu --set full --clock-control none, one proof, MSMs serialised)",
-            "kernel_rev": meta.get("kernel_rev"), "config": meta.get("config"),
+            "kernel_rev": meta.get("kernel_rev"), "config": meta.get("config"), "curve": meta.get("curve"), "log_n": meta.get("log_n"),
+            "workload": "synthetic",
             "g1_dram_bytes_per_launch": stage["dram"] if stage["done"] else None, "g1_stage_ms_under_ncu": stage["ms"],
             "note": "DRAM bytes (read + write) summed over the kernels of the G1 accumulation stage (batched-affine rounds + "
                     "msm_accum_l0) of the first full-density G1 MSM of the proof"}

@@ -13,8 +13,16 @@
 #include "../../include/g16b200.h"
 #include "fp.cuh"
 
+// The same file also builds, with a plain host compiler, as the stand-alone groth16_b200/libg16workload.so
+// (-DG16_WORKLOAD_STANDALONE; Makefile): bench.py's `--impl reference` arm and anything else that only needs a circuit can then
+// generate it without loading the CUDA library at all.
 namespace g16 {
+#ifdef G16_WORKLOAD_STANDALONE
+static thread_local std::string g_workload_err;
+static int fail(int code, const std::string& msg) { g_workload_err = msg; return code; }
+#else
 int fail(int code, const std::string& msg);
+#endif
 
 static inline uint64_t splitmix(uint64_t& s) {
   s += 0x9E3779B97F4A7C15ull;
@@ -68,6 +76,9 @@ static int synth(uint32_t log_n, uint64_t seed, uint32_t* a_col, uint64_t* a_val
 }
 }  // namespace g16
 
+#ifdef G16_WORKLOAD_STANDALONE
+extern "C" const char* g16_workload_last_error() { return g16::g_workload_err.c_str(); }
+#endif
 extern "C" int g16_synthetic_r1cs(int curve, uint32_t log_n, uint64_t seed, uint32_t* a_col, uint64_t* a_val, uint32_t* b_col,
                                   uint32_t* c_col, uint64_t* full_assignment) {
   using namespace g16;

@@ -37,6 +37,22 @@ def _fr(gen, r):
             return v
 
 
+_WORKLOAD_LIB = None
+
+
+def _workload_lib():
+    """groth16_b200/libg16workload.so: csrc/workload.cu built with the host compiler alone (same generator, no CUDA runtime).
+    Preferred when present, so that a process that only needs a circuit -- bench.py's `--impl reference` arm -- never maps the
+    CUDA library; falls back to the copy inside libg16b200.so."""
+    global _WORKLOAD_LIB
+    if _WORKLOAD_LIB is None:
+        import ctypes as C
+        import os
+        p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libg16workload.so")
+        _WORKLOAD_LIB = C.CDLL(p) if os.path.exists(p) else False
+    return _WORKLOAD_LIB or None
+
+
 def synthetic_r1cs(curve, log_n: int, seed: int = 0, num_inputs: int = 1):
     """The synthetic R1CS of SURVEY.md section 8d through g16_synthetic_r1cs (csrc/workload.cu: host code of the library, no
     GPU needed; a Python loop over 2^24 constraints would take minutes).  One public input."""
@@ -57,8 +73,16 @@ def synthetic_r1cs(curve, log_n: int, seed: int = 0, num_inputs: int = 1):
     c_col = np.empty(nc, dtype=np.uint32)
     z = np.zeros((ninst + nwit, 4), dtype=np.uint64)
     vp = lambda x: x.ctypes.data_as(C.c_void_p)
-    rc = _lib.load().g16_synthetic_r1cs(c.cid, log_n, seed & 0xFFFFFFFFFFFFFFFF, vp(a_col), vp(a_val), vp(b_col), vp(c_col), vp(z))
+    lib = _workload_lib()
+    fn = (lib or _lib.load()).g16_synthetic_r1cs
+    if lib is not None:
+        fn.argtypes = [C.c_int, C.c_uint32, C.c_uint64] + [C.c_void_p] * 5
+        fn.restype = C.c_int
+    rc = fn(c.cid, log_n, seed & 0xFFFFFFFFFFFFFFFF, vp(a_col), vp(a_val), vp(b_col), vp(c_col), vp(z))
     if rc != 0:
+        if lib is not None:
+            lib.g16_workload_last_error.restype = C.c_char_p
+            raise ValueError(lib.g16_workload_last_error().decode())
         raise ValueError(_lib.last_error())
     one = np.ascontiguousarray(cd.fr.enc1(1))
     a_rp = np.arange(0, 2 * nc + 1, 2, dtype=np.uint32)

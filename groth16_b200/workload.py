@@ -49,7 +49,10 @@ def _workload_lib():
         import ctypes as C
         import os
         p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libg16workload.so")
-        _WORKLOAD_LIB = C.CDLL(p) if os.path.exists(p) else False
+        try:
+            _WORKLOAD_LIB = C.CDLL(p) if os.path.exists(p) else False
+        except OSError:          # unloadable on this host: the copy inside libg16b200.so serves
+            _WORKLOAD_LIB = False
     return _WORKLOAD_LIB or None
 
 

@@ -30,6 +30,17 @@ def main():
                                              "024aa2b2f08f0a91260805272dc51051c6e47ad4fa403b02b4510b647ae3d1770bac0326a805bbefd48056c8c121bdb8",
         "mont_inv64": {"bls12_381": ["0xfffffffeffffffff", "0x89f3fffcfffcfffd"], "bn254": ["0xc2e1f593efffffff", "0x87d20782e4866389"],
                        "bls12_377": ["0x0a117fffffffffff", "0x8508bfffffffffff"]},
+        # alt_bn128 / BN254: generator (1, 2) and its double as published with EIP-196 (ecAdd / ecMul test vectors), the G2
+        # generator of EIP-197; the G1 generator of ark-bls12-377 (curves/g1.rs G1_GENERATOR_X / _Y)
+        "bn254_g1_generator": ["0x1", "0x2"],
+        "bn254_two_g1_eip196": ["0x030644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd3",
+                                "0x15ed738c0e0a7c92e7845f96b2ae9c0a68a6a449e3538fc7ff3ebf7a5a18a2c4"],
+        "bn254_g2_generator_eip197": [["0x1800deef121f1e76426a00665e5c4479674322d4f75edadd46debd5cd992f6ed",
+                                       "0x198e9393920d483a7260bfb731fb5d25f1aa493335a9e71297e485b7aef312c2"],
+                                      ["0x12c85ea5db8c6deb4aab71808dcb408fe3d1e7690c43d37b4ce6cc0166fa7daa",
+                                       "0x090689d0585ff075ec9e99ad690c3395bc4b313370b38ef355acdadcd122975b"]],
+        "bls12_377_g1_generator_ark": ["0x008848defe740a67c8fc6225bf87ff5485951e2caa9d41bb188282c8bd37cb5cd5481512ffcd394eeab9b16eb21be9ef",
+                                       "0x01914a69c5102eff1f674f5d30afeec4bd7fb348ca3e52d96d182ad44fb82305c2fe3d3634a9591afd82de55559c8ea6"],
     }, "oracle": {}, "seeds": SEEDS}
     for name, c in P.CURVES.items():
         cx = P.ctx(c)

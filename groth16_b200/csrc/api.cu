@@ -25,7 +25,11 @@ bool NcclApi::load() {
   if (!h)
     for (const char* n : names)
       if ((h = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
-  if (!h) { err = std::string("dlopen(libnccl.so.2): ") + (dlerror() ? dlerror() : "not found"); return false; }
+  if (!h) {
+    const char* why = dlerror();   // one call: dlerror() clears the message it returns
+    err = std::string("dlopen(libnccl.so.2): ") + (why ? why : "not found");
+    return false;
+  }
   auto sym = [&](const char* n) { return dlsym(h, n); };
   GetUniqueId = reinterpret_cast<int (*)(NcclUniqueId*)>(sym("ncclGetUniqueId"));
   CommInitRank = reinterpret_cast<int (*)(void**, int, NcclUniqueId, int)>(sym("ncclCommInitRank"));

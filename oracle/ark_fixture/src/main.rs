@@ -23,7 +23,7 @@ use ark_relations::{
     r1cs::{ConstraintMatrices, ConstraintSynthesizer, ConstraintSystem, ConstraintSystemRef, OptimizationGoal, SynthesisError, Variable},
 };
 use ark_serialize::CanonicalSerialize;
-use ark_snark::SNARK;
+use ark_crypto_primitives::snark::SNARK; // the trait ark-groth16 implements (src/lib.rs:47,59)
 use ark_std::rand::{rngs::StdRng, Rng, SeedableRng};
 use std::{fs, io::Write, path::Path};
 
